@@ -1,0 +1,199 @@
+/*
+ * ndtb.h — C ABI of the B200-native NDT registration engine (libndtb.so).
+ *
+ * Drop-in boundary for the NDT hot path of MalcolmMielle/ndt_feature_graph.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference checkout; "[upstream]"
+ * = perception_oru symbol the reference calls but does not vendor):
+ *
+ *   ndtb_map_*           lslgeneric::NDTMap(new LazyGrid(res)) + loadPointCloud/addPointCloud/
+ *                        computeNDTCells [upstream]; call sites
+ *                        ndt_feature/src/ndt_feature_src/ndt_feature_fuser_hmt.cpp:87-94,195-227,485-486
+ *   ndtb_d2d_derivatives NDTMatcherD2D::derivativesNDT [upstream]; call sites
+ *                        ndt_feature/include/ndt_feature/ndt_matcher_d2d_fusion.h:80,238,444,617,856,1085
+ *   ndtb_d2d_match       NDTMatcherD2D::match(NDTMap&,NDTMap&,Affine3d&,bool) [upstream]; call site
+ *                        ndt_feature/src/ndt_feature_src/ndt_feature_graph.cpp:273
+ *   ndtb_fusion_match    ndt_feature::matchFusion, ndt_matcher_d2d_fusion.h:797-1155 (useNDT only)
+ *   ndtb_d2d_covariance  NDTMatcherD2D::covariance [upstream]; call sites ndt_feature_graph.cpp:298,
+ *                        ndt_feature_fuser_hmt.cpp:405
+ *   ndtb_d2d_match_batch NDTFeatureGraph::updateLinksUsingNDTRegistration, ndt_feature_graph.cpp:347-353
+ *                        (the serial loop over links becomes one batched launch)
+ *   ndtb_register_scans  NDTFeatureFuserHMT::update front-end step, ndt_feature_fuser_hmt.cpp:195-227
+ *                        (local map of the scan) + :356-357 (match) + :399-420 (covariance), batched
+ *   ndtb_overlap_score   NDTFeatureNode::overlapNDTOccupancyScore, ndt_feature/include/ndt_feature/ndt_feature_node.h:213-252
+ *
+ * Conventions
+ *   - plain C types only; poses are 16 doubles, column-major 4x4 (Eigen::Affine3d::matrix().data()).
+ *   - every function returns an int: 0 = NDTB_OK, <0 = error (ndtb_strerror).  Nothing throws across
+ *     the ABI, nothing blocks on stdin (cf. ndt_feature_graph.cpp:318-328), nothing prints.
+ *   - a ndtb_ctx is single-owner (one per host thread / per GPU); calls are synchronous at return
+ *     unless every output lives in device memory (NDTB_MEM_DEVICE), in which case work is only
+ *     enqueued on the context's stream.
+ *   - there is NO CPU implementation behind this ABI: without a CUDA device every compute entry
+ *     point fails with NDTB_ERR_CUDA.
+ */
+#ifndef NDTB_H
+#define NDTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDTB_VERSION 100
+
+enum {
+  NDTB_OK = 0,
+  NDTB_ERR_CUDA = -1,      /* CUDA runtime error / no device */
+  NDTB_ERR_ARG = -2,       /* bad argument */
+  NDTB_ERR_GRID = -3,      /* grid undefined or too large (> 2^31 voxels) */
+  NDTB_ERR_EMPTY = -4,     /* no usable points / no Gaussian cells */
+  NDTB_ERR_SINGULAR = -5,  /* 6x6 system not invertible (covariance, Tcov) */
+  NDTB_ERR_NOMEM = -6
+};
+
+enum { NDTB_MEM_HOST = 0, NDTB_MEM_DEVICE = 1 };
+
+typedef struct ndtb_ctx ndtb_ctx;
+typedef struct ndtb_map ndtb_map; /* lslgeneric::NDTMap on a LazyGrid, resident in HBM */
+
+typedef struct ndtb_grid { /* LazyGrid geometry */
+  double center[3];        /* centerX/Y/Z */
+  double cell[3];          /* cellSizeX/Y/Z */
+  int32_t size[3];         /* sizeX/Y/Z in cells = |ceil(size_m / cell)| */
+} ndtb_grid;
+
+typedef struct ndtb_cell { /* NDTCell snapshot (same layout as the oracle's orc_cell) */
+  double mean[3];
+  double cov[6];           /* xx, xy, xz, yy, yz, zz */
+  int32_t n;               /* NDTCell::N */
+  int32_t has_gaussian;    /* NDTCell::hasGaussian_ */
+  int32_t idx[3];          /* voxel index in the LazyGrid */
+  float occ;               /* log-odds occupancy */
+} ndtb_cell;
+
+typedef struct ndtb_params { /* NDTMatcherD2D public knobs + matchFusion flags */
+  int32_t n_neighbours;    /* NDTMatcherD2D::n_neighbours (2) */
+  int32_t itr_max;         /* ITR_MAX (30) */
+  int32_t step_control;    /* 1 */
+  int32_t regularize;      /* 1 */
+  double delta_score;      /* DELTA_SCORE (1e-3 for a default-constructed matcher) */
+  double lfd1, lfd2;       /* 1, 0.05 */
+  int32_t use_soft_constraints; /* matchFusion only */
+  int32_t use_tikhonov;         /* matchFusion only */
+  int32_t ctas_per_match;  /* engine knob: CTAs (one thread-block cluster) cooperating on one registration;
+                              0 = auto (1 for batches >= #SMs, up to 8 for small batches) */
+  int32_t pad_;
+} ndtb_params;
+
+/* ndtb_result.status bits (SURVEY.md §5 "failure detection") */
+enum {
+  NDTB_ST_CONVERGED = 1,   /* match() returned true */
+  NDTB_ST_ITR_MAX = 2,     /* ITR_MAX exceeded (match() returned false) */
+  NDTB_ST_POSE_CHANGED = 4,/* T differs bitwise from the initial guess (ndt_feature_graph.cpp:286-294) */
+  NDTB_ST_NONFINITE = 8,   /* a non-finite score/gradient was met */
+  NDTB_ST_NO_CELLS = 16    /* source or target has no Gaussian cells */
+};
+
+typedef struct ndtb_result {
+  double T[16];            /* column-major 4x4 */
+  double score;            /* final score_here */
+  double score_best;
+  int32_t converged;       /* return value of match() */
+  int32_t iterations;
+  int32_t n_hess_passes;   /* derivativesNDT calls with Hessian */
+  int32_t n_grad_passes;   /* gradient-only derivativesNDT calls */
+  int32_t pose_changed;
+  int32_t exit_code;       /* 0 loop end, 1 gradient vanished, 2 dginit>0, 3 itr_max, 4 no regularisation */
+  int32_t status;          /* NDTB_ST_* */
+  int32_t n_src_cells;     /* Gaussian cells of the source map (Cs) */
+  int32_t n_tgt_cells;     /* Gaussian cells of the target map (Ct) */
+  int32_t tgt_table_entries; /* 16-byte entries of the target's block table (probe window W) */
+} ndtb_result;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int ndtb_version(void);
+const char *ndtb_strerror(int code);
+const char *ndtb_last_error(const ndtb_ctx *ctx); /* text of the last CUDA error on this context */
+/* device = CUDA ordinal. stream = cudaStream_t to enqueue on (NULL: the context creates its own). */
+int ndtb_ctx_create(int device, void *stream, ndtb_ctx **out);
+void ndtb_ctx_destroy(ndtb_ctx *ctx);
+int ndtb_ctx_synchronize(ndtb_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+int64_t ndtb_ctx_launch_count(const ndtb_ctx *ctx);
+int ndtb_ctx_sm_count(const ndtb_ctx *ctx);
+/* Device-time accounting of the dominant kernel (bench.py roofline): when enabled, every launch of the
+ * registration kernel is bracketed by CUDA events on the context's stream.  ndtb_ctx_match_time synchronises,
+ * returns the accumulated milliseconds and launch count since the last call, and resets both. */
+int ndtb_ctx_enable_timing(ndtb_ctx *ctx, int on);
+int ndtb_ctx_match_time(ndtb_ctx *ctx, double *ms, int64_t *launches);
+void ndtb_default_params(ndtb_params *p);
+
+/* ---- maps: lslgeneric::NDTMap(new LazyGrid(cell)) --------------------------------------------- */
+int ndtb_map_create(ndtb_ctx *ctx, double cell_x, double cell_y, double cell_z, ndtb_map **out);
+void ndtb_map_destroy(ndtb_map *m);
+/* NDTMap::guessSize(cx,cy,cz,sx,sy,sz) (floats upstream) — ndt_feature_fuser_hmt.cpp:222 */
+int ndtb_map_guess_size(ndtb_map *m, double cx, double cy, double cz, double sx, double sy, double sz);
+/* NDTMap::setMapSize(sx,sy,sz) */
+int ndtb_map_set_map_size(ndtb_map *m, double sx, double sy, double sz);
+/* NDTMap::initialize(cx,cy,cz,sx,sy,sz) — ndt_feature_fuser_hmt.cpp:89 */
+int ndtb_map_initialize(ndtb_map *m, double cx, double cy, double cz, double sx, double sy, double sz);
+/* NDTMap::loadPointCloud(pc, range_limit): (re)defines the grid, bins the points.  pts = n x 4 float
+ * (pcl::PointXYZ: x,y,z,pad), in host or device memory.  *n_binned (optional) = points kept. */
+int ndtb_map_load_point_cloud(ndtb_map *m, const float *pts, int64_t n, double range_limit, int mem,
+                              int64_t *n_binned);
+/* NDTMap::addPointCloud, end-point binning only (no ray tracing — SURVEY.md §8f rank 1) */
+int ndtb_map_add_points(ndtb_map *m, const float *pts, int64_t n, int mem, int64_t *n_binned);
+/* NDTMap::computeNDTCells(CELL_UPDATE_MODE_SAMPLE_VARIANCE, maxnumpoints, occupancy_limit) */
+int ndtb_map_compute_cells(ndtb_map *m, uint32_t maxnumpoints, float occupancy_limit);
+/* Batched loadPointCloud + computeNDTCells over n_maps maps in a handful of launches (front-end and
+ * bench path).  pts[i] / n_pts[i] per map; all pointers in the same memory space `mem`. */
+int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, const float *const *pts,
+                         const int64_t *n_pts, double range_limit, int mem, uint32_t maxnumpoints,
+                         float occupancy_limit);
+/* Build directly from cells (JFF fixtures / NDTMapMsg): placed by the voxel of their mean unless use_idx. */
+int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells, int64_t n, int use_idx);
+int ndtb_map_grid(const ndtb_map *m, ndtb_grid *g);
+int64_t ndtb_map_num_cells(const ndtb_map *m, int gaussian_only);
+/* cells sorted by linear voxel index ((ix*sy)+iy)*sz+iz; returns the number available */
+int64_t ndtb_map_export_cells(const ndtb_map *m, ndtb_cell *out, int64_t cap, int gaussian_only);
+/* LazyGrid::getIndexForPoint for n points (parity hook): out = n x 3 int32, INT32_MIN for NaN points;
+ * returns the number of in-bounds points or <0 */
+int64_t ndtb_map_point_indices(const ndtb_map *m, const float *pts, int64_t n, int mem, int32_t *out);
+
+/* ---- NDTMatcherD2D ---------------------------------------------------------------------------- */
+/* derivativesNDT of the source cells moved by T against the target map.
+ * out43 = score, g[6], H[36] row-major (H zero when !want_hessian); n_pairs optional. */
+int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T,
+                         const ndtb_params *p, int want_hessian, double *out43, int64_t *n_pairs);
+int ndtb_d2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0,
+                   const ndtb_params *p, ndtb_result *res);
+/* matchFusion with useNDT=true, useFeat=false: soft constraint Q = Tcov^-1 (Tcov36 row-major 6x6) */
+int ndtb_fusion_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0,
+                      const double *Tcov36, const ndtb_params *p, ndtb_result *res);
+/* covariance(target, source, T, cov) -> cov36 row-major */
+int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T,
+                        const ndtb_params *p, double *cov36);
+/* n_edges independent registrations in one launch.  T0s = n_edges x 16.  with_covariance follows
+ * ndt_feature_graph.cpp:286-310 (covariance() only if the pose changed, else 0.02*I).
+ * res / cov36s (n_edges x 36, may be NULL) live in `out_mem` memory. */
+int ndtb_d2d_match_batch(ndtb_ctx *ctx, int64_t n_edges, const ndtb_map *const *tgt,
+                         const ndtb_map *const *src, const double *T0s, const ndtb_params *p,
+                         int with_covariance, int out_mem, ndtb_result *res, double *cov36s);
+
+/* Batched front-end step: for each pair build the NDT map of the target scan and of the source scan
+ * (cell size `cell`, guess-size grids unless map_size[0..2] > 0: then setMapSize), register source onto
+ * target from T0s, optionally compute the covariance.  Point pointers in `in_mem`, outputs in `out_mem`. */
+int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_pts, const int64_t *n_tgt,
+                        const float *const *src_pts, const int64_t *n_src, const double *T0s, double cell,
+                        const double *map_size, double range_limit, const ndtb_params *p,
+                        int with_covariance, int in_mem, int out_mem, ndtb_result *res, double *cov36s);
+
+/* ndt_feature::overlapNDTOccupancyScore(ref, mov, T) */
+int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T,
+                       double *score);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDTB_H */

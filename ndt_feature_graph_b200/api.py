@@ -1,0 +1,404 @@
+"""ctypes host mirror of the reference's NDT interface on top of the C ABI (include/ndtb.h).
+
+Names and argument meaning follow the reference call sites:
+  NDTMap(LazyGrid(res))                 ndt_feature_fuser_hmt.cpp:87,196
+  .initialize / .guessSize / .setMapSize / .loadPointCloud / .addPointCloud / .computeNDTCells
+                                        ndt_feature_fuser_hmt.cpp:89-94,201-227,485-486
+  NDTMatcherD2D().match / .covariance   ndt_feature_graph.cpp:261-298
+  .derivativesNDT                       ndt_matcher_d2d_fusion.h:856
+  matchFusion                           ndt_matcher_d2d_fusion.h:797-1155
+Poses are 4x4 numpy arrays (Eigen::Affine3d).  Everything computes on the GPU; a missing library or
+device raises NdtbError (never a silent CPU path).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST, DEVICE = 0, 1
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libndtb.so")
+
+
+class NdtbError(RuntimeError):
+    pass
+
+
+class Grid(C.Structure):
+    _fields_ = [("center", C.c_double * 3), ("cell", C.c_double * 3), ("size", C.c_int32 * 3)]
+
+
+CELL_DTYPE = np.dtype(
+    [("mean", "<f8", 3), ("cov", "<f8", 6), ("n", "<i4"), ("has_gaussian", "<i4"), ("idx", "<i4", 3), ("occ", "<f4")],
+    align=True,
+)
+assert CELL_DTYPE.itemsize == 96
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("n_neighbours", C.c_int32),
+        ("itr_max", C.c_int32),
+        ("step_control", C.c_int32),
+        ("regularize", C.c_int32),
+        ("delta_score", C.c_double),
+        ("lfd1", C.c_double),
+        ("lfd2", C.c_double),
+        ("use_soft_constraints", C.c_int32),
+        ("use_tikhonov", C.c_int32),
+        ("ctas_per_match", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("T", C.c_double * 16),
+        ("score", C.c_double),
+        ("score_best", C.c_double),
+        ("converged", C.c_int32),
+        ("iterations", C.c_int32),
+        ("n_hess_passes", C.c_int32),
+        ("n_grad_passes", C.c_int32),
+        ("pose_changed", C.c_int32),
+        ("exit_code", C.c_int32),
+        ("status", C.c_int32),
+        ("n_src_cells", C.c_int32),
+        ("n_tgt_cells", C.c_int32),
+        ("tgt_table_entries", C.c_int32),
+    ]
+
+    def pose(self):
+        return np.array(self.T, dtype=np.float64).reshape(4, 4).T.copy()
+
+
+RESULT_DTYPE = np.dtype(
+    [("T", "<f8", 16), ("score", "<f8"), ("score_best", "<f8"), ("converged", "<i4"), ("iterations", "<i4"),
+     ("n_hess_passes", "<i4"), ("n_grad_passes", "<i4"), ("pose_changed", "<i4"), ("exit_code", "<i4"),
+     ("status", "<i4"), ("n_src_cells", "<i4"), ("n_tgt_cells", "<i4"), ("tgt_table_entries", "<i4")]
+)
+assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 184
+
+_lib = None
+
+
+def load_library():
+    """dlopen lib/libndtb.so and declare the ABI.  Raises NdtbError when the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise NdtbError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(path)
+    vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+    PP, PR = C.POINTER(Params), C.POINTER(Result)
+    sig = {
+        "ndtb_version": (C.c_int, []),
+        "ndtb_strerror": (C.c_char_p, [C.c_int]),
+        "ndtb_last_error": (C.c_char_p, [vp]),
+        "ndtb_ctx_create": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+        "ndtb_ctx_destroy": (None, [vp]),
+        "ndtb_ctx_synchronize": (C.c_int, [vp]),
+        "ndtb_ctx_launch_count": (i64, [vp]),
+        "ndtb_ctx_sm_count": (C.c_int, [vp]),
+        "ndtb_ctx_enable_timing": (C.c_int, [vp, C.c_int]),
+        "ndtb_ctx_match_time": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(i64)]),
+        "ndtb_default_params": (None, [PP]),
+        "ndtb_map_create": (C.c_int, [vp, dbl, dbl, dbl, C.POINTER(vp)]),
+        "ndtb_map_destroy": (None, [vp]),
+        "ndtb_map_guess_size": (C.c_int, [vp] + [dbl] * 6),
+        "ndtb_map_set_map_size": (C.c_int, [vp] + [dbl] * 3),
+        "ndtb_map_initialize": (C.c_int, [vp] + [dbl] * 6),
+        "ndtb_map_load_point_cloud": (C.c_int, [vp, vp, i64, dbl, C.c_int, C.POINTER(i64)]),
+        "ndtb_map_add_points": (C.c_int, [vp, vp, i64, C.c_int, C.POINTER(i64)]),
+        "ndtb_map_compute_cells": (C.c_int, [vp, C.c_uint32, C.c_float]),
+        "ndtb_map_build_batch": (C.c_int, [vp, i64, vp, vp, vp, dbl, C.c_int, C.c_uint32, C.c_float]),
+        "ndtb_map_from_cells": (C.c_int, [vp, C.POINTER(Grid), vp, i64, C.c_int]),
+        "ndtb_map_grid": (C.c_int, [vp, C.POINTER(Grid)]),
+        "ndtb_map_num_cells": (i64, [vp, C.c_int]),
+        "ndtb_map_export_cells": (i64, [vp, vp, i64, C.c_int]),
+        "ndtb_map_point_indices": (i64, [vp, vp, i64, C.c_int, vp]),
+        "ndtb_d2d_derivatives": (C.c_int, [vp, vp, vp, vp, PP, C.c_int, vp, C.POINTER(i64)]),
+        "ndtb_d2d_match": (C.c_int, [vp, vp, vp, vp, PP, PR]),
+        "ndtb_fusion_match": (C.c_int, [vp, vp, vp, vp, vp, PP, PR]),
+        "ndtb_d2d_covariance": (C.c_int, [vp, vp, vp, vp, PP, vp]),
+        "ndtb_d2d_match_batch": (C.c_int, [vp, i64, vp, vp, vp, PP, C.c_int, C.c_int, vp, vp]),
+        "ndtb_register_scans": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, dbl, vp, dbl, PP, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "ndtb_overlap_score": (C.c_int, [vp, vp, vp, vp, C.POINTER(dbl)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    L._abi = sorted(sig)
+    _lib = L
+    return L
+
+
+def abi_symbols():
+    return load_library()._abi
+
+
+def _cm(T):
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float64).T).ravel().copy()
+
+
+def _pts4(pts):
+    pts = np.asarray(pts, dtype=np.float32)
+    if pts.ndim != 2 or pts.shape[1] not in (3, 4):
+        raise ValueError("points must be [n,3] or [n,4]")
+    if pts.shape[1] == 3:
+        pts = np.concatenate([pts, np.zeros((pts.shape[0], 1), np.float32)], axis=1)
+    return np.ascontiguousarray(pts)
+
+
+class Engine:
+    """One ndtb_ctx: a GPU + a stream.  Single owner (one per host thread / per GPU)."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.ndtb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise NdtbError(f"ndtb_ctx_create(device={device}) failed: {self.L.ndtb_strerror(rc).decode()}")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ndtb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise NdtbError(f"{self.L.ndtb_strerror(rc).decode()} [{self.L.ndtb_last_error(self.h).decode()}]")
+
+    def synchronize(self):
+        self.check(self.L.ndtb_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.ndtb_ctx_launch_count(self.h))
+
+    @property
+    def sm_count(self):
+        return int(self.L.ndtb_ctx_sm_count(self.h))
+
+    def enable_timing(self, on=True):
+        self.check(self.L.ndtb_ctx_enable_timing(self.h, int(on)))
+
+    def match_time(self):
+        """(milliseconds, launches) of the registration kernel since the last call (synchronises)."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        self.check(self.L.ndtb_ctx_match_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def register_scans_raw(self, n, tgt_ptrs, n_tgt, src_ptrs, n_src, T0s_cm, cell, range_limit, params, with_covariance,
+                           in_mem, out_mem, res_ptr, cov_ptr):
+        """Pointer-level ndtb_register_scans (bench.py: device-resident inputs / outputs)."""
+        self.check(self.L.ndtb_register_scans(self.h, n, tgt_ptrs, n_tgt, src_ptrs, n_src, T0s_cm, cell, None, range_limit,
+                                              C.byref(params), int(with_covariance), in_mem, out_mem, res_ptr, cov_ptr))
+
+    def default_params(self, **kw):
+        p = Params()
+        self.L.ndtb_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    # ---- batched entry points -------------------------------------------------------------
+    def build_maps(self, maps, clouds, range_limit=-1.0, maxnumpoints=0xFFFFFFFF, occupancy_limit=255.0):
+        """loadPointCloud + computeNDTCells for many maps in a handful of launches (host clouds)."""
+        n = len(maps)
+        cl = [_pts4(c) for c in clouds]
+        mh = (C.c_void_p * n)(*[m.h for m in maps])
+        ph = (C.c_void_p * n)(*[c.ctypes.data for c in cl])
+        nn = (C.c_int64 * n)(*[c.shape[0] for c in cl])
+        self.check(self.L.ndtb_map_build_batch(self.h, n, mh, ph, nn, range_limit, HOST, maxnumpoints, occupancy_limit))
+
+    def match_batch(self, tgts, srcs, T0s, params=None, with_covariance=False):
+        """NDTFeatureGraph::updateLinksUsingNDTRegistration (ndt_feature_graph.cpp:347-353) as one launch."""
+        p = params or self.default_params()
+        n = len(tgts)
+        ta = (C.c_void_p * n)(*[m.h for m in tgts])
+        sa = (C.c_void_p * n)(*[m.h for m in srcs])
+        Tc = np.concatenate([_cm(T) for T in T0s]) if n else np.zeros(0)
+        res = np.zeros(n, RESULT_DTYPE)
+        cov = np.zeros((n, 36))
+        self.check(self.L.ndtb_d2d_match_batch(self.h, n, ta, sa, Tc.ctypes.data, C.byref(p), int(with_covariance), HOST,
+                                               res.ctypes.data, cov.ctypes.data if with_covariance else None))
+        return res, cov.reshape(n, 6, 6)
+
+    def register_scans(self, tgt_clouds, src_clouds, T0s, cell=0.5, map_size=None, range_limit=-1.0, params=None,
+                       with_covariance=False):
+        """Front-end step for a batch of scan pairs from HOST clouds: build both local maps, match, covariance."""
+        p = params or self.default_params()
+        n = len(tgt_clouds)
+        tc = [_pts4(c) for c in tgt_clouds]
+        sc = [_pts4(c) for c in src_clouds]
+        tp = (C.c_void_p * n)(*[c.ctypes.data for c in tc])
+        sp = (C.c_void_p * n)(*[c.ctypes.data for c in sc])
+        tn = (C.c_int64 * n)(*[c.shape[0] for c in tc])
+        sn = (C.c_int64 * n)(*[c.shape[0] for c in sc])
+        Tc = np.concatenate([_cm(T) for T in T0s])
+        ms = np.asarray(map_size, dtype=np.float64) if map_size is not None else None
+        res = np.zeros(n, RESULT_DTYPE)
+        cov = np.zeros((n, 36))
+        self.check(self.L.ndtb_register_scans(self.h, n, tp, tn, sp, sn, Tc.ctypes.data, cell,
+                                              ms.ctypes.data if ms is not None else None, range_limit, C.byref(p),
+                                              int(with_covariance), HOST, HOST, res.ctypes.data,
+                                              cov.ctypes.data if with_covariance else None))
+        return res, cov.reshape(n, 6, 6)
+
+
+class LazyGrid:
+    """lslgeneric::LazyGrid(cellSize): only carries the resolution, the grid lives in the NDTMap."""
+
+    def __init__(self, cell_size):
+        self.cell = (cell_size,) * 3 if np.isscalar(cell_size) else tuple(cell_size)
+
+
+class NDTMap:
+    """lslgeneric::NDTMap(new LazyGrid(res)) resident in HBM."""
+
+    def __init__(self, engine, index=0.5):
+        self.e = engine
+        cell = index.cell if isinstance(index, LazyGrid) else LazyGrid(index).cell
+        h = C.c_void_p()
+        engine.check(engine.L.ndtb_map_create(engine.h, *cell, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and getattr(self.e, "h", None):
+                self.e.L.ndtb_map_destroy(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    def guessSize(self, cx, cy, cz, sx, sy, sz):
+        self.e.check(self.e.L.ndtb_map_guess_size(self.h, cx, cy, cz, sx, sy, sz))
+
+    def setMapSize(self, sx, sy, sz):
+        self.e.check(self.e.L.ndtb_map_set_map_size(self.h, sx, sy, sz))
+
+    def initialize(self, cx, cy, cz, sx, sy, sz):
+        self.e.check(self.e.L.ndtb_map_initialize(self.h, cx, cy, cz, sx, sy, sz))
+
+    def loadPointCloud(self, pts, range_limit=-1.0, want_count=True):
+        pts = _pts4(pts)
+        nb = C.c_int64(0)
+        self.e.check(self.e.L.ndtb_map_load_point_cloud(self.h, pts.ctypes.data, pts.shape[0], range_limit, HOST,
+                                                        C.byref(nb) if want_count else None))
+        return nb.value
+
+    def addPointCloud(self, pts, want_count=True):
+        """End-point binning part of NDTMap::addPointCloud (no free-space ray tracing)."""
+        pts = _pts4(pts)
+        nb = C.c_int64(0)
+        self.e.check(self.e.L.ndtb_map_add_points(self.h, pts.ctypes.data, pts.shape[0], HOST,
+                                                  C.byref(nb) if want_count else None))
+        return nb.value
+
+    def computeNDTCells(self, maxnumpoints=int(1e9), occupancy_limit=255.0):
+        self.e.check(self.e.L.ndtb_map_compute_cells(self.h, int(maxnumpoints), float(occupancy_limit)))
+
+    def from_cells(self, center, cell, size, cells, use_idx=False):
+        g = Grid((C.c_double * 3)(*center), (C.c_double * 3)(*cell), (C.c_int32 * 3)(*[int(s) for s in size]))
+        cells = np.ascontiguousarray(cells, dtype=CELL_DTYPE)
+        self.e.check(self.e.L.ndtb_map_from_cells(self.h, C.byref(g), cells.ctypes.data, cells.shape[0], int(use_idx)))
+        return self
+
+    def grid(self):
+        g = Grid()
+        self.e.check(self.e.L.ndtb_map_grid(self.h, C.byref(g)))
+        return np.array(g.center), np.array(g.cell), np.array(g.size)
+
+    def numberOfActiveCells(self):
+        return int(self.e.L.ndtb_map_num_cells(self.h, 1))
+
+    def num_cells(self, gaussian_only=True):
+        return int(self.e.L.ndtb_map_num_cells(self.h, int(gaussian_only)))
+
+    def export_cells(self, gaussian_only=True):
+        n = self.num_cells(False)
+        out = np.zeros(max(n, 1), dtype=CELL_DTYPE)
+        k = self.e.L.ndtb_map_export_cells(self.h, out.ctypes.data, n, int(gaussian_only))
+        if k < 0:
+            self.e.check(int(k))
+        return out[:k].copy()
+
+    def point_indices(self, pts):
+        pts = _pts4(pts)
+        out = np.zeros((pts.shape[0], 3), np.int32)
+        k = self.e.L.ndtb_map_point_indices(self.h, pts.ctypes.data, pts.shape[0], HOST, out.ctypes.data)
+        if k < 0:
+            self.e.check(int(k))
+        return out, int(k)
+
+    def overlapNDTOccupancyScore(self, mov, T):
+        """ndt_feature::overlapNDTOccupancyScore(ref=self, mov, T) (ndt_feature_node.h:213-252)."""
+        s = C.c_double(0)
+        Tc = _cm(T)
+        self.e.check(self.e.L.ndtb_overlap_score(self.e.h, self.h, mov.h, Tc.ctypes.data, C.byref(s)))
+        return s.value
+
+
+class NDTMatcherD2D:
+    """lslgeneric::NDTMatcherD2D with its public knobs (ndt_feature_graph.cpp:261-262)."""
+
+    def __init__(self, engine, **knobs):
+        self.e = engine
+        self.params = engine.default_params(**knobs)
+
+    @property
+    def n_neighbours(self):
+        return self.params.n_neighbours
+
+    @n_neighbours.setter
+    def n_neighbours(self, v):
+        self.params.n_neighbours = int(v)
+
+    def derivativesNDT(self, target, source, T, computeHessian=True):
+        """score, gradient[6], Hessian[6,6], n_pairs of the source cells moved by T against the target map."""
+        out = np.zeros(43)
+        Tc = _cm(T)
+        npairs = C.c_int64(0)
+        self.e.check(self.e.L.ndtb_d2d_derivatives(self.e.h, target.h, source.h, Tc.ctypes.data, C.byref(self.params),
+                                                   int(computeHessian), out.ctypes.data, C.byref(npairs)))
+        return out[0], out[1:7].copy(), out[7:].reshape(6, 6).copy(), npairs.value
+
+    def match(self, target, source, T, useInitialGuess=True):
+        """Returns the Result (res.pose() is the refined T, res.converged the bool upstream returns)."""
+        T0 = np.asarray(T, dtype=np.float64) if useInitialGuess else np.eye(4)
+        r = Result()
+        Tc = _cm(T0)
+        self.e.check(self.e.L.ndtb_d2d_match(self.e.h, target.h, source.h, Tc.ctypes.data, C.byref(self.params), C.byref(r)))
+        return r
+
+    def matchFusion(self, target, source, T, Tcov):
+        """ndt_feature::matchFusion with useNDT only (soft constraint / Tikhonov from self.params)."""
+        r = Result()
+        Tc = _cm(T)
+        cov = np.ascontiguousarray(Tcov, dtype=np.float64)
+        self.e.check(self.e.L.ndtb_fusion_match(self.e.h, target.h, source.h, Tc.ctypes.data, cov.ctypes.data,
+                                                C.byref(self.params), C.byref(r)))
+        return r
+
+    def covariance(self, target, source, T):
+        out = np.zeros(36)
+        Tc = _cm(T)
+        rc = self.e.L.ndtb_d2d_covariance(self.e.h, target.h, source.h, Tc.ctypes.data, C.byref(self.params), out.ctypes.data)
+        if rc not in (0, -5):
+            self.e.check(rc)
+        return rc == 0, out.reshape(6, 6)

@@ -1,0 +1,1027 @@
+// api.cu — the extern "C" ABI of include/ndtb.h: contexts, HBM-resident maps, batched map build and
+// batched registration.  Host code only orchestrates (allocation, job tables, launches); all arithmetic
+// is in map_build.cu (kernel i) and d2d.cu (kernel ii + optimiser).  There is no CPU compute path here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ndtb.h"
+#include "engine.cuh"
+#include "map_build.cuh"
+
+namespace ndtb {
+// d2d.cu
+size_t match_smem_bytes(int table_entries);
+cudaError_t launch_match(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, ndtb_result *d_out, cudaStream_t stream);
+cudaError_t launch_derivatives(const MatchJob *d_job, const MatchConfig &cfg, bool hess, int n_ctas, double *d_partial,
+                               double *d_out29, cudaStream_t stream);
+cudaError_t launch_covariance(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, const ndtb_result *d_res,
+                              const long long *d_gt_off, double *d_gt, double *d_partial, int n_chunks, double *d_cov36,
+                              int *d_status, cudaStream_t stream);
+int cov_partial_width();
+int acc_total();
+}  // namespace ndtb
+
+using namespace ndtb;
+
+struct ndtb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  int smem_optin = 0;
+  int64_t launches = 0;
+  std::string last_error;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;  // event pairs around match-kernel launches
+};
+
+#define CU_TRY(ctx, expr)                                                                           \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+      return NDTB_ERR_CUDA;                                                                         \
+    }                                                                                               \
+  } while (0)
+
+namespace {
+
+struct Slab {  // one stream-ordered device allocation shared by the maps of a batch
+  ndtb_ctx *ctx;
+  char *p = nullptr;
+  size_t bytes = 0;
+  Slab(ndtb_ctx *c) : ctx(c) {}
+  ~Slab() {
+    if (p) cudaFreeAsync(p, ctx->stream);
+  }
+};
+using SlabP = std::shared_ptr<Slab>;
+
+int slab_alloc(ndtb_ctx *ctx, size_t bytes, SlabP &out) {
+  out = std::make_shared<Slab>(ctx);
+  out->bytes = bytes ? bytes : 256;
+  CU_TRY(ctx, cudaMallocAsync((void **)&out->p, out->bytes, ctx->stream));
+  return NDTB_OK;
+}
+
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  }
+};
+
+}  // namespace
+
+struct ndtb_map {
+  ndtb_ctx *ctx;
+  double cell[3];
+  // NDTMap members [upstream]
+  bool guess_size = true;
+  double centerx = 0, centery = 0, centerz = 0;
+  double map_sizex = -1, map_sizey = -1, map_sizez = -1;
+  bool is_first_load = true;
+  bool grid_ready = false;
+  GridDesc g;
+  int nblk = 0;
+  // pending points (loadPointCloud / addPointCloud before computeNDTCells)
+  struct Chunk {
+    SlabP buf;
+    int n;
+  };
+  std::vector<Chunk> pending;
+  bool pending_load = false;  // pending points came from loadPointCloud (fresh map)
+  bool pending_built = false; // ... and their cells were already computed (with occupancy limit pending_occ)
+  float pending_occ = 255.f;
+  double pending_range = -1.0;
+  // all-cells structure
+  SlabP s_blocks, s_cells;
+  unsigned long long *amask = nullptr;
+  int *abase = nullptr, *tb_list = nullptr, *counts = nullptr;
+  int n_all = 0, ntb = 0;
+  double *cmean = nullptr, *ccov = nullptr;
+  int *cn = nullptr, *chas = nullptr;
+  float *cocc = nullptr;
+  // Gaussian view
+  double *gcell = nullptr;
+  int *g2c = nullptr;
+  HashEntry *table = nullptr;
+  int tsize = 0, ng = 0, ngb = 0;
+  int64_t last_binned = 0;
+
+  void set_grid(double cx, double cy, double cz, double sx, double sy, double sz) {
+    g.center[0] = cx, g.center[1] = cy, g.center[2] = cz;
+    const double sm[3] = {sx, sy, sz};
+    for (int i = 0; i < 3; i++) {
+      g.cell[i] = cell[i];
+      g.size[i] = (int32_t)std::abs(std::ceil(sm[i] / cell[i]));  // LazyGrid::setSize
+      g.nb[i] = (g.size[i] + 3) / 4;
+    }
+    grid_ready = true;
+    drop_cells();
+  }
+  void drop_cells() {
+    s_blocks.reset(), s_cells.reset();
+    amask = nullptr, abase = nullptr, tb_list = nullptr, counts = nullptr;
+    cmean = ccov = nullptr, cn = chas = nullptr, cocc = nullptr, gcell = nullptr, g2c = nullptr, table = nullptr;
+    n_all = ntb = tsize = ng = ngb = 0;
+  }
+  int64_t nblocks() const { return (int64_t)g.nb[0] * g.nb[1] * g.nb[2]; }
+};
+
+namespace {
+
+struct PointSrc {
+  const float4 *dev;  // device pointer
+  int n;
+};
+
+// fill a MapView for the matcher
+MapView view_of(const ndtb_map *m) {
+  MapView v;
+  v.g = m->g;
+  v.gcell = m->gcell;
+  v.table = m->table;
+  v.ng = m->ng;
+  v.tsize = m->tsize;
+  return v;
+}
+
+// NDTMap::loadPointCloud [upstream], grid part: guess_size -> centre = centroid of the usable points, size = setMapSize
+// values or (4 maxDist, 4 maxDist, 3 (maxz - minz)); else the guessSize()/initialize() values.  empty[i] = no usable point.
+int define_grids(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::vector<PointSrc> &pts,
+                 const std::vector<double> &range, std::vector<char> &empty) {
+  const int M = (int)maps.size();
+  cudaStream_t st = ctx->stream;
+  empty.assign(M, 0);
+  std::vector<int> which;
+  for (int i = 0; i < M; i++)
+    if (maps[i]->guess_size) which.push_back(i);
+  if (!which.empty()) {
+    const int W = (int)which.size();
+    std::vector<BuildJob> jobs(W);
+    std::memset(jobs.data(), 0, sizeof(BuildJob) * W);
+    std::vector<int> ident(W);
+    int max_pts = 1;
+    for (int w = 0; w < W; w++) {
+      jobs[w].pts = pts[which[w]].dev, jobs[w].npts = pts[which[w]].n, jobs[w].range_limit = range[which[w]];
+      ident[w] = w;
+      max_pts = std::max(max_pts, jobs[w].npts);
+    }
+    Carver c;
+    const size_t o_j = c.take(sizeof(BuildJob) * W), o_gs = c.take(64 * (size_t)W), o_w = c.take(4 * (size_t)W);
+    SlabP s;
+    if (int rc = slab_alloc(ctx, c.off, s)) return rc;
+    std::vector<double> gs(8 * (size_t)W);
+    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_j, jobs.data(), sizeof(BuildJob) * W, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_w, ident.data(), 4 * (size_t)W, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemsetAsync(s->p + o_gs, 0, 64 * (size_t)W, st));
+    ctx->launches += launch_guess((const BuildJob *)(s->p + o_j), (const int *)(s->p + o_w), W, max_pts, (double *)(s->p + o_gs), st);
+    CU_TRY(ctx, cudaMemcpyAsync(gs.data(), s->p + o_gs, 64 * (size_t)W, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    auto unkey = [](double bits) {
+      unsigned long long k;
+      std::memcpy(&k, &bits, 8);
+      const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+      double v;
+      std::memcpy(&v, &b, 8);
+      return v;
+    };
+    for (int w = 0; w < W; w++) {
+      ndtb_map *m = maps[which[w]];
+      const double *o = &gs[8 * (size_t)w];
+      if (o[3] <= 0) {
+        empty[which[w]] = 1;
+        m->grid_ready = false;
+        m->drop_cells();
+        continue;
+      }
+      const double maxDist = o[4], maxz = unkey(o[5]), minz = unkey(o[6]);
+      if (m->map_sizex > 0 && m->map_sizey > 0 && m->map_sizez > 0)
+        m->set_grid(o[0], o[1], o[2], m->map_sizex, m->map_sizey, m->map_sizez);
+      else
+        m->set_grid(o[0], o[1], o[2], 4 * maxDist, 4 * maxDist, 3 * (maxz - minz));
+      m->is_first_load = false;
+    }
+  }
+  for (int i = 0; i < M; i++) {
+    ndtb_map *m = maps[i];
+    if (!m->guess_size) {
+      m->set_grid(m->centerx, m->centery, m->centerz, m->map_sizex, m->map_sizey, m->map_sizez);
+      m->is_first_load = false;
+    }
+  }
+  return NDTB_OK;
+}
+
+// Batched (load|add)PointCloud + computeNDTCells.  pts[i] are device pointers that stay valid during the call.
+// load[i]: 1 = loadPointCloud semantics (grid (re)defined, map emptied), 2 = fresh map on the grid it already has,
+//          0 = addPointCloud (merge into the existing cells).
+int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::vector<PointSrc> &pts,
+                const std::vector<char> &load, const std::vector<double> &range, uint32_t maxnumpoints, float occ_limit) {
+  const int M = (int)maps.size();
+  if (M == 0) return NDTB_OK;
+  cudaStream_t st = ctx->stream;
+  std::vector<BuildJob> jobs(M);
+  std::memset(jobs.data(), 0, sizeof(BuildJob) * M);
+  int max_pts = 1;
+  for (int i = 0; i < M; i++) {
+    jobs[i].pts = pts[i].dev;
+    jobs[i].npts = pts[i].n;
+    jobs[i].range_limit = load[i] ? range[i] : -1.0;
+    jobs[i].maxnumpoints = maxnumpoints;
+    jobs[i].occ_limit = occ_limit;
+    jobs[i].log_occ = std::log(0.6 / (1.0 - 0.6));
+    max_pts = std::max(max_pts, pts[i].n);
+  }
+  SlabP s_jobs;
+  if (int rc = slab_alloc(ctx, sizeof(BuildJob) * M, s_jobs)) return rc;
+  BuildJob *d_jobs = (BuildJob *)s_jobs->p;
+
+  // ---- phase A: grids
+  std::vector<char> empty(M, 0);
+  {
+    std::vector<ndtb_map *> lm;
+    std::vector<PointSrc> lp;
+    std::vector<double> lr;
+    std::vector<int> li;
+    for (int i = 0; i < M; i++)
+      if (load[i] == 1) lm.push_back(maps[i]), lp.push_back(pts[i]), lr.push_back(range[i]), li.push_back(i);
+    std::vector<char> le;
+    if (!lm.empty()) {
+      if (int rc = define_grids(ctx, lm, lp, lr, le)) return rc;
+      for (size_t q = 0; q < li.size(); q++) empty[li[q]] = le[q];
+    }
+  }
+  for (int i = 0; i < M; i++) {
+    ndtb_map *m = maps[i];
+    if (load[i] == 2) {
+      if (!m->grid_ready) empty[i] = 1;
+      else m->drop_cells();
+    }
+    if (empty[i]) {
+      m->drop_cells();
+      m->last_binned = 0;
+      continue;
+    }
+    if (!m->grid_ready) return NDTB_ERR_GRID;
+    if (m->nblocks() <= 0 || m->nblocks() * 64 >= ((int64_t)1 << 31)) return NDTB_ERR_GRID;
+    m->nblk = (int)m->nblocks();
+  }
+
+  // ---- phase B: mark touched voxels, number the cells
+  std::vector<SlabP> keep_old;  // previous storage of merged maps stays alive until the end of the build
+  Carver cb, ct;
+  struct OffB {
+    size_t amask, abase, tbl, counts, ptc, seg, seg2;
+  };
+  std::vector<OffB> ob(M);
+  for (int i = 0; i < M; i++) {
+    if (empty[i]) continue;
+    ndtb_map *m = maps[i];
+    const int64_t tb_cap = std::min<int64_t>(m->nblk, (int64_t)m->n_all + pts[i].n);
+    ob[i].amask = cb.take(8 * (size_t)m->nblk);
+    ob[i].abase = cb.take(4 * (size_t)m->nblk);
+    ob[i].tbl = cb.take(4 * (size_t)std::max<int64_t>(tb_cap, 1));
+    ob[i].counts = cb.take(32);
+    ob[i].ptc = ct.take(4 * (size_t)pts[i].n);
+    ob[i].seg = ct.take(4 * (size_t)pts[i].n);
+    ob[i].seg2 = ct.take(4 * (size_t)pts[i].n);
+  }
+  SlabP s_b, s_t;
+  if (int rc = slab_alloc(ctx, cb.off, s_b)) return rc;
+  if (int rc = slab_alloc(ctx, ct.off, s_t)) return rc;
+  CU_TRY(ctx, cudaMemsetAsync(s_b->p, 0, s_b->bytes, st));
+  for (int i = 0; i < M; i++) {
+    if (empty[i]) continue;
+    ndtb_map *m = maps[i];
+    BuildJob &j = jobs[i];
+    j.g = m->g;
+    j.nblk = m->nblk;
+    j.amask = (unsigned long long *)(s_b->p + ob[i].amask);
+    j.abase = (int *)(s_b->p + ob[i].abase);
+    j.tb_list = (int *)(s_b->p + ob[i].tbl);
+    j.counts = (int *)(s_b->p + ob[i].counts);
+    j.pt_cell = (int *)(s_t->p + ob[i].ptc);
+    j.seg_idx = (int *)(s_t->p + ob[i].seg);
+    j.seg2 = (int *)(s_t->p + ob[i].seg2);
+    if (m->n_all > 0) {  // merge: start from the cells the map already has
+      j.o_amask = m->amask, j.o_abase = m->abase, j.o_cmean = m->cmean, j.o_ccov = m->ccov;
+      j.o_cn = m->cn, j.o_chas = m->chas, j.o_cocc = m->cocc;
+      CU_TRY(ctx, cudaMemcpyAsync(j.amask, m->amask, 8 * (size_t)m->nblk, cudaMemcpyDeviceToDevice, st));
+      keep_old.push_back(m->s_blocks), keep_old.push_back(m->s_cells);
+    }
+  }
+  std::vector<BuildJob> live;  // only non-empty maps are launched
+  std::vector<int> live_idx;
+  for (int i = 0; i < M; i++)
+    if (!empty[i]) live.push_back(jobs[i]), live_idx.push_back(i);
+  const int L = (int)live.size();
+  if (L == 0) return NDTB_OK;
+  CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
+  ctx->launches += launch_mark(d_jobs, L, max_pts, st);
+  std::vector<int> cnts(8 * (size_t)L);
+  for (int l = 0; l < L; l++)
+    CU_TRY(ctx, cudaMemcpyAsync(&cnts[8 * l], live[l].counts, 32, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+
+  // ---- phase C: cell records + Gaussian view
+  Carver cc, ct2;
+  struct OffC {
+    size_t mean, cov, n, has, occ, gcell, g2c, table, cnt, segoff, cursor, gmask, gbase;
+  };
+  std::vector<OffC> oc(L);
+  int max_ntb = 1;
+  for (int l = 0; l < L; l++) {
+    const int n_all = cnts[8 * l], ntb = cnts[8 * l + 1];
+    max_ntb = std::max(max_ntb, ntb);
+    int tsize = 2;
+    while (tsize < 2 * ntb) tsize <<= 1;
+    live[l].n_all = n_all;
+    live[l].tsize = tsize;
+    const size_t na = (size_t)std::max(n_all, 1);
+    oc[l].mean = cc.take(24 * na), oc[l].cov = cc.take(72 * na), oc[l].n = cc.take(4 * na), oc[l].has = cc.take(4 * na);
+    oc[l].occ = cc.take(4 * na), oc[l].gcell = cc.take(72 * na), oc[l].g2c = cc.take(4 * na);
+    oc[l].table = cc.take(sizeof(HashEntry) * (size_t)tsize);
+    oc[l].cnt = ct2.take(4 * na), oc[l].segoff = ct2.take(4 * na), oc[l].cursor = ct2.take(4 * na);
+    oc[l].gmask = ct2.take(8 * (size_t)std::max(ntb, 1)), oc[l].gbase = ct2.take(4 * (size_t)std::max(ntb, 1));
+  }
+  SlabP s_c, s_t2;
+  if (int rc = slab_alloc(ctx, cc.off, s_c)) return rc;
+  if (int rc = slab_alloc(ctx, ct2.off, s_t2)) return rc;
+  CU_TRY(ctx, cudaMemsetAsync(s_t2->p, 0, s_t2->bytes, st));
+  for (int l = 0; l < L; l++) {
+    BuildJob &j = live[l];
+    j.cmean = (double *)(s_c->p + oc[l].mean), j.ccov = (double *)(s_c->p + oc[l].cov);
+    j.cn = (int *)(s_c->p + oc[l].n), j.chas = (int *)(s_c->p + oc[l].has), j.cocc = (float *)(s_c->p + oc[l].occ);
+    j.gcell = (double *)(s_c->p + oc[l].gcell), j.g2c = (int *)(s_c->p + oc[l].g2c);
+    j.table = (HashEntry *)(s_c->p + oc[l].table);
+    j.cnt = (int *)(s_t2->p + oc[l].cnt), j.seg_off = (int *)(s_t2->p + oc[l].segoff), j.cursor = (int *)(s_t2->p + oc[l].cursor);
+    j.gmask_t = (unsigned long long *)(s_t2->p + oc[l].gmask), j.gbase_t = (int *)(s_t2->p + oc[l].gbase);
+    CU_TRY(ctx, cudaMemsetAsync(j.table, 0xFF, sizeof(HashEntry) * (size_t)j.tsize, st));
+  }
+  CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
+  ctx->launches += launch_cells(d_jobs, L, max_pts, max_ntb, st);
+  ctx->launches += launch_gview(d_jobs, L, max_ntb, st);
+  for (int l = 0; l < L; l++)
+    CU_TRY(ctx, cudaMemcpyAsync(&cnts[8 * l], live[l].counts, 32, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  for (int l = 0; l < L; l++) {
+    ndtb_map *m = maps[live_idx[l]];
+    const BuildJob &j = live[l];
+    m->s_blocks = s_b, m->s_cells = s_c;
+    m->amask = j.amask, m->abase = j.abase, m->tb_list = j.tb_list, m->counts = j.counts;
+    m->n_all = cnts[8 * l], m->ntb = cnts[8 * l + 1], m->ng = cnts[8 * l + 2], m->ngb = cnts[8 * l + 3];
+    m->last_binned = cnts[8 * l + 4];
+    m->cmean = j.cmean, m->ccov = j.ccov, m->cn = j.cn, m->chas = j.chas, m->cocc = j.cocc;
+    m->gcell = j.gcell, m->g2c = j.g2c, m->table = j.table, m->tsize = j.tsize;
+  }
+  return NDTB_OK;
+}
+
+// device copy of host/device points
+int stage_points(ndtb_ctx *ctx, const float *pts, int64_t n, int mem, SlabP &out) {
+  if (int rc = slab_alloc(ctx, 16 * (size_t)std::max<int64_t>(n, 1), out)) return rc;
+  if (n > 0)
+    CU_TRY(ctx, cudaMemcpyAsync(out->p, pts, 16 * (size_t)n, mem == NDTB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                ctx->stream));
+  return NDTB_OK;
+}
+
+MatchConfig make_config(const ndtb_ctx *ctx, const ndtb_params *p, int max_tsize) {
+  MatchConfig c;
+  c.n_neighbours = p->n_neighbours;
+  c.itr_max = p->itr_max, c.step_control = p->step_control, c.regularize = p->regularize;
+  c.soft = p->use_soft_constraints, c.tik = p->use_tikhonov;
+  c.delta_score = p->delta_score, c.lfd1 = p->lfd1, c.lfd2 = p->lfd2;
+  // stage the block table in shared memory when it fits next to the optimiser state
+  int cap = (int)((ctx->smem_optin - (int)match_smem_bytes(0) - 1024) / (int)sizeof(HashEntry));
+  if (cap < 0) cap = 0;
+  c.table_smem_entries = max_tsize <= cap ? max_tsize : 0;
+  if (max_tsize > cap) {  // largest power of two that fits: smaller maps of the batch still get staged
+    int t = 1;
+    while (2 * t <= cap) t <<= 1;
+    c.table_smem_entries = cap >= 2 ? t : 0;
+  }
+  return c;
+}
+
+void fill_job(MatchJob &j, const ndtb_map *tgt, const ndtb_map *src, const double *T0, const double *Q36) {
+  std::memset(&j, 0, sizeof j);
+  j.tgt = view_of(tgt);
+  j.src_gcell = src->gcell;
+  j.src_ng = src->ng;
+  std::memcpy(j.T0, T0, sizeof j.T0);
+  j.fusion = Q36 != nullptr;
+  if (Q36) std::memcpy(j.Q, Q36, sizeof j.Q);
+}
+
+bool map_ok(const ndtb_map *m) { return m && m->grid_ready; }
+
+// a map without any cell still needs valid pointers for the kernels: give it a 2-entry empty table
+int ensure_view(ndtb_ctx *ctx, ndtb_map *m) {
+  if (m->table) return NDTB_OK;
+  SlabP s;
+  if (int rc = slab_alloc(ctx, 256, s)) return rc;
+  CU_TRY(ctx, cudaMemsetAsync(s->p, 0xFF, 256, ctx->stream));
+  m->s_cells = s;
+  m->table = (HashEntry *)s->p;
+  m->tsize = 2;
+  m->gcell = (double *)(s->p + 64);
+  m->ng = 0;
+  return NDTB_OK;
+}
+
+int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const ndtb_map *const *src, const double *T0s,
+                     const double *Q36s /*n x 36 or null*/, const ndtb_params *p, int with_cov, int out_mem, ndtb_result *res,
+                     double *cov36s) {
+  if (n <= 0) return NDTB_OK;
+  cudaStream_t st = ctx->stream;
+  std::vector<MatchJob> jobs((size_t)n);
+  int max_tsize = 2;
+  size_t gt_total = 0;
+  std::vector<long long> gt_off((size_t)n);
+  for (int64_t e = 0; e < n; e++) {
+    if (!map_ok(tgt[e]) || !map_ok(src[e])) return NDTB_ERR_GRID;
+    if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(tgt[e]))) return rc;
+    if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(src[e]))) return rc;
+    fill_job(jobs[e], tgt[e], src[e], T0s + 16 * e, Q36s ? Q36s + 36 * e : nullptr);
+    max_tsize = std::max(max_tsize, tgt[e]->tsize);
+    gt_off[e] = (long long)gt_total;
+    gt_total += (size_t)std::max(tgt[e]->ng, 1);
+  }
+  const MatchConfig cfg = make_config(ctx, p, max_tsize);
+  const int n_chunks = 8;
+  Carver c;
+  const size_t o_jobs = c.take(sizeof(MatchJob) * n), o_res = c.take(sizeof(ndtb_result) * n);
+  const size_t o_goff = c.take(8 * n), o_gt = c.take(with_cov ? 48 * gt_total : 0);
+  const size_t o_part = c.take(with_cov ? 8 * (size_t)cov_partial_width() * n_chunks * n : 0);
+  const size_t o_cov = c.take(with_cov ? 288 * (size_t)n : 0), o_stat = c.take(4 * n);
+  SlabP s;
+  if (int rc = slab_alloc(ctx, c.off, s)) return rc;
+  MatchJob *d_jobs = (MatchJob *)(s->p + o_jobs);
+  ndtb_result *d_res = out_mem == NDTB_MEM_DEVICE ? res : (ndtb_result *)(s->p + o_res);
+  CU_TRY(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(MatchJob) * n, cudaMemcpyHostToDevice, st));
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx->timing) {
+    CU_TRY(ctx, cudaEventCreate(&ev0));
+    CU_TRY(ctx, cudaEventCreate(&ev1));
+    CU_TRY(ctx, cudaEventRecord(ev0, st));
+  }
+  CU_TRY(ctx, launch_match(d_jobs, (int)n, cfg, d_res, st));
+  ctx->launches += 1;
+  if (ctx->timing) {
+    CU_TRY(ctx, cudaEventRecord(ev1, st));
+    ctx->timed.push_back({ev0, ev1});
+  }
+  if (with_cov && cov36s) {
+    double *d_cov = out_mem == NDTB_MEM_DEVICE ? cov36s : (double *)(s->p + o_cov);
+    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_goff, gt_off.data(), 8 * n, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemsetAsync(s->p + o_gt, 0, 48 * gt_total, st));
+    CU_TRY(ctx, launch_covariance(d_jobs, (int)n, cfg, d_res, (const long long *)(s->p + o_goff), (double *)(s->p + o_gt),
+                                  (double *)(s->p + o_part), n_chunks, d_cov, (int *)(s->p + o_stat), st));
+    ctx->launches += 2;
+    if (out_mem != NDTB_MEM_DEVICE)
+      CU_TRY(ctx, cudaMemcpyAsync(cov36s, d_cov, 288 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  if (out_mem != NDTB_MEM_DEVICE) {
+    CU_TRY(ctx, cudaMemcpyAsync(res, d_res, sizeof(ndtb_result) * n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+  }
+  return NDTB_OK;
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+extern "C" {
+
+int ndtb_version(void) { return NDTB_VERSION; }
+
+const char *ndtb_strerror(int code) {
+  switch (code) {
+    case NDTB_OK: return "ok";
+    case NDTB_ERR_CUDA: return "CUDA error or no CUDA device (this engine has no CPU path)";
+    case NDTB_ERR_ARG: return "bad argument";
+    case NDTB_ERR_GRID: return "grid undefined or too large";
+    case NDTB_ERR_EMPTY: return "no usable points / cells";
+    case NDTB_ERR_SINGULAR: return "singular 6x6 system";
+    case NDTB_ERR_NOMEM: return "out of memory";
+    default: return "unknown error";
+  }
+}
+
+const char *ndtb_last_error(const ndtb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int ndtb_ctx_create(int device, void *stream, ndtb_ctx **out) {
+  if (!out) return NDTB_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return NDTB_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return NDTB_ERR_CUDA;
+  ndtb_ctx *c = new ndtb_ctx();
+  c->device = device;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return NDTB_ERR_CUDA;
+    }
+    c->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;  // keep freed slabs cached: allocation becomes a pointer bump after warm-up
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = c;
+  return NDTB_OK;
+}
+
+void ndtb_ctx_destroy(ndtb_ctx *ctx) {
+  if (!ctx) return;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int ndtb_ctx_synchronize(ndtb_ctx *ctx) {
+  if (!ctx) return NDTB_ERR_ARG;
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NDTB_OK;
+}
+int64_t ndtb_ctx_launch_count(const ndtb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int ndtb_ctx_enable_timing(ndtb_ctx *ctx, int on) {
+  if (!ctx) return NDTB_ERR_ARG;
+  ctx->timing = on != 0;
+  return NDTB_OK;
+}
+int ndtb_ctx_match_time(ndtb_ctx *ctx, double *ms, int64_t *launches) {
+  if (!ctx || !ms) return NDTB_ERR_ARG;
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  double tot = 0;
+  for (auto &pr : ctx->timed) {
+    float t = 0;
+    CU_TRY(ctx, cudaEventElapsedTime(&t, pr.first, pr.second));
+    tot += t;
+    cudaEventDestroy(pr.first), cudaEventDestroy(pr.second);
+  }
+  *ms = tot;
+  if (launches) *launches = (int64_t)ctx->timed.size();
+  ctx->timed.clear();
+  return NDTB_OK;
+}
+int ndtb_ctx_sm_count(const ndtb_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+void ndtb_default_params(ndtb_params *p) {
+  p->n_neighbours = 2;
+  p->itr_max = 30;
+  p->step_control = 1;
+  p->regularize = 1;
+  p->delta_score = 10e-3 * 0.1;  // upstream init(): DELTA_SCORE = 10e-3 * current_resolution(0.1)
+  p->lfd1 = 1;
+  p->lfd2 = 0.05;
+  p->use_soft_constraints = 0;
+  p->use_tikhonov = 0;
+  p->ctas_per_match = 0;
+  p->pad_ = 0;
+}
+
+// ---- maps
+int ndtb_map_create(ndtb_ctx *ctx, double cx, double cy, double cz, ndtb_map **out) {
+  if (!ctx || !out || !(cx > 0 && cy > 0 && cz > 0)) return NDTB_ERR_ARG;
+  ndtb_map *m = new ndtb_map();
+  m->ctx = ctx;
+  m->cell[0] = cx, m->cell[1] = cy, m->cell[2] = cz;
+  std::memset(&m->g, 0, sizeof m->g);
+  *out = m;
+  return NDTB_OK;
+}
+void ndtb_map_destroy(ndtb_map *m) { delete m; }
+
+int ndtb_map_guess_size(ndtb_map *m, double cx, double cy, double cz, double sx, double sy, double sz) {
+  if (!m) return NDTB_ERR_ARG;
+  m->guess_size = false;  // NDTMap::guessSize takes floats upstream
+  m->centerx = (float)cx, m->centery = (float)cy, m->centerz = (float)cz;
+  m->map_sizex = (float)sx, m->map_sizey = (float)sy, m->map_sizez = (float)sz;
+  return NDTB_OK;
+}
+int ndtb_map_set_map_size(ndtb_map *m, double sx, double sy, double sz) {
+  if (!m) return NDTB_ERR_ARG;
+  m->map_sizex = (float)sx, m->map_sizey = (float)sy, m->map_sizez = (float)sz;
+  return NDTB_OK;
+}
+int ndtb_map_initialize(ndtb_map *m, double cx, double cy, double cz, double sx, double sy, double sz) {
+  if (!m) return NDTB_ERR_ARG;
+  m->is_first_load = false;
+  m->guess_size = false;
+  m->centerx = cx, m->centery = cy, m->centerz = cz;
+  m->map_sizex = sx, m->map_sizey = sy, m->map_sizez = sz;
+  m->set_grid(cx, cy, cz, sx, sy, sz);
+  if (m->nblocks() <= 0 || m->nblocks() * 64 >= ((int64_t)1 << 31)) return NDTB_ERR_GRID;
+  return NDTB_OK;
+}
+
+int ndtb_map_load_point_cloud(ndtb_map *m, const float *pts, int64_t n, double range_limit, int mem, int64_t *n_binned) {
+  if (!m || n < 0 || n > 0x7fffffff || (n > 0 && !pts)) return NDTB_ERR_ARG;
+  ndtb_ctx *ctx = m->ctx;
+  SlabP buf;
+  if (int rc = stage_points(ctx, pts, n, mem, buf)) return rc;
+  m->pending.clear();
+  m->pending.push_back({buf, (int)n});
+  m->pending_load = true;
+  m->pending_range = range_limit;
+  m->pending_built = false;
+  std::vector<ndtb_map *> maps{m};
+  std::vector<PointSrc> ps{{(const float4 *)buf->p, (int)n}};
+  std::vector<char> empty;
+  if (int rc = define_grids(ctx, maps, ps, {range_limit}, empty)) return rc;
+  if (n_binned) {
+    // the count needs the binning: build now with the default limits; computeNDTCells with the same
+    // occupancy limit is then a no-op (maxnumpoints only matters when merging into existing cells)
+    if (int rc = build_batch(ctx, maps, ps, {2}, {range_limit}, 0xffffffffu, 255.f)) return rc;
+    m->pending_built = true;
+    m->pending_occ = 255.f;
+    *n_binned = m->last_binned;
+  }
+  return NDTB_OK;
+}
+
+int ndtb_map_add_points(ndtb_map *m, const float *pts, int64_t n, int mem, int64_t *n_binned) {
+  if (!m || n < 0 || n > 0x7fffffff || (n > 0 && !pts)) return NDTB_ERR_ARG;
+  if (!m->grid_ready) return NDTB_ERR_GRID;
+  ndtb_ctx *ctx = m->ctx;
+  SlabP buf;
+  if (int rc = stage_points(ctx, pts, n, mem, buf)) return rc;
+  if (m->pending_load && m->pending_built) {  // a loadPointCloud whose cells were already computed
+    m->pending.clear();
+    m->pending_load = false;
+  }
+  m->pending.push_back({buf, (int)n});
+  if (n_binned) {
+    *n_binned = 0;
+    if (n > 0) {
+      const int64_t r = ndtb_map_point_indices(m, (const float *)buf->p, n, NDTB_MEM_DEVICE + 1, nullptr);
+      if (r < 0) return (int)r;
+      *n_binned = r;
+    }
+  }
+  return NDTB_OK;
+}
+
+int ndtb_map_compute_cells(ndtb_map *m, uint32_t maxnumpoints, float occupancy_limit) {
+  if (!m) return NDTB_ERR_ARG;
+  ndtb_ctx *ctx = m->ctx;
+  if (m->pending.empty()) return NDTB_OK;
+  if (m->pending_load && m->pending_built && occupancy_limit == m->pending_occ) {
+    m->pending.clear();
+    m->pending_load = false;
+    return NDTB_OK;
+  }
+  // concatenate the pending chunks in arrival order (= NDTCell::points_ insertion order)
+  int64_t total = 0;
+  for (auto &c : m->pending) total += c.n;
+  if (total > 0x7fffffff) return NDTB_ERR_ARG;
+  SlabP all;
+  const float4 *ptr;
+  if (m->pending.size() == 1) {
+    all = m->pending[0].buf;
+    ptr = (const float4 *)all->p;
+  } else {
+    if (int rc = slab_alloc(ctx, 16 * (size_t)std::max<int64_t>(total, 1), all)) return rc;
+    size_t off = 0;
+    for (auto &c : m->pending) {
+      CU_TRY(ctx, cudaMemcpyAsync(all->p + off, c.buf->p, 16 * (size_t)c.n, cudaMemcpyDeviceToDevice, ctx->stream));
+      off += 16 * (size_t)c.n;
+    }
+    ptr = (const float4 *)all->p;
+  }
+  const char load = m->pending_load ? 2 : 0;
+  std::vector<ndtb_map *> maps{m};
+  std::vector<PointSrc> ps{{ptr, (int)total}};
+  const int rc = build_batch(ctx, maps, ps, {load}, {m->pending_range}, maxnumpoints, occupancy_limit);
+  m->pending.clear();
+  m->pending_load = false;
+  return rc;
+}
+
+int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, const float *const *pts, const int64_t *n_pts,
+                         double range_limit, int mem, uint32_t maxnumpoints, float occupancy_limit) {
+  if (!ctx || n_maps < 0 || (n_maps > 0 && (!maps || !pts || !n_pts))) return NDTB_ERR_ARG;
+  std::vector<ndtb_map *> mv((size_t)n_maps);
+  std::vector<PointSrc> ps((size_t)n_maps);
+  std::vector<SlabP> staged;
+  SlabP big;
+  if (mem != NDTB_MEM_DEVICE) {  // one slab, one H2D copy per scan
+    Carver c;
+    std::vector<size_t> off((size_t)n_maps);
+    for (int64_t i = 0; i < n_maps; i++) off[i] = c.take(16 * (size_t)n_pts[i]);
+    if (int rc = slab_alloc(ctx, c.off, big)) return rc;
+    for (int64_t i = 0; i < n_maps; i++) {
+      if (n_pts[i] > 0)
+        CU_TRY(ctx, cudaMemcpyAsync(big->p + off[i], pts[i], 16 * (size_t)n_pts[i], cudaMemcpyHostToDevice, ctx->stream));
+      ps[i] = {(const float4 *)(big->p + off[i]), (int)n_pts[i]};
+    }
+  }
+  for (int64_t i = 0; i < n_maps; i++) {
+    if (!maps[i] || n_pts[i] < 0 || n_pts[i] > 0x7fffffff) return NDTB_ERR_ARG;
+    mv[i] = maps[i];
+    if (mem == NDTB_MEM_DEVICE) ps[i] = {(const float4 *)pts[i], (int)n_pts[i]};
+    maps[i]->pending.clear();
+    maps[i]->pending_load = false;
+  }
+  std::vector<char> load((size_t)n_maps, 1);
+  std::vector<double> range((size_t)n_maps, range_limit);
+  return build_batch(ctx, mv, ps, load, range, maxnumpoints, occupancy_limit);
+}
+
+int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells, int64_t n, int use_idx) {
+  if (!m || !g || n < 0 || (n > 0 && !cells)) return NDTB_ERR_ARG;
+  ndtb_ctx *ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  for (int i = 0; i < 3; i++) {
+    m->cell[i] = g->cell[i];
+    m->g.cell[i] = g->cell[i], m->g.center[i] = g->center[i], m->g.size[i] = g->size[i], m->g.nb[i] = (g->size[i] + 3) / 4;
+  }
+  m->guess_size = false, m->is_first_load = false, m->grid_ready = true;
+  m->drop_cells();
+  m->pending.clear();
+  if (m->nblocks() <= 0 || m->nblocks() * 64 >= ((int64_t)1 << 31)) return NDTB_ERR_GRID;
+  m->nblk = (int)m->nblocks();
+  Carver cb, ct;
+  const size_t o_amask = cb.take(8 * (size_t)m->nblk), o_abase = cb.take(4 * (size_t)m->nblk);
+  const size_t o_tbl = cb.take(4 * (size_t)std::max<int64_t>(std::min<int64_t>(m->nblk, n), 1)), o_counts = cb.take(32);
+  const size_t o_cells = ct.take(sizeof(ndtb_cell) * (size_t)std::max<int64_t>(n, 1)), o_vox = ct.take(4 * (size_t)std::max<int64_t>(n, 1));
+  const size_t o_err = ct.take(4), o_job = ct.take(sizeof(BuildJob));
+  SlabP s_b, s_t;
+  if (int rc = slab_alloc(ctx, cb.off, s_b)) return rc;
+  if (int rc = slab_alloc(ctx, ct.off, s_t)) return rc;
+  CU_TRY(ctx, cudaMemsetAsync(s_b->p, 0, s_b->bytes, st));
+  CU_TRY(ctx, cudaMemsetAsync(s_t->p + o_err, 0, 4, st));
+  if (n > 0) CU_TRY(ctx, cudaMemcpyAsync(s_t->p + o_cells, cells, sizeof(ndtb_cell) * (size_t)n, cudaMemcpyHostToDevice, st));
+  BuildJob j;
+  std::memset(&j, 0, sizeof j);
+  j.g = m->g, j.nblk = m->nblk;
+  j.amask = (unsigned long long *)(s_b->p + o_amask), j.abase = (int *)(s_b->p + o_abase);
+  j.tb_list = (int *)(s_b->p + o_tbl), j.counts = (int *)(s_b->p + o_counts);
+  BuildJob *d_job = (BuildJob *)(s_t->p + o_job);
+  const ndtb_cell *d_cells = (const ndtb_cell *)(s_t->p + o_cells);
+  int *d_vox = (int *)(s_t->p + o_vox), *d_err = (int *)(s_t->p + o_err);
+  CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, st));
+  ctx->launches += launch_from_cells_voxel(d_job, d_cells, (int)n, use_idx, d_vox, d_err, st);
+  ctx->launches += launch_blockscan(d_job, 1, st);
+  int cnts[8], err = 0;
+  CU_TRY(ctx, cudaMemcpyAsync(cnts, j.counts, 32, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  if (err) return NDTB_ERR_ARG;  // a cell outside the grid (the CPU restatement returns -1)
+  const int n_all = cnts[0], ntb = cnts[1];
+  int tsize = 2;
+  while (tsize < 2 * ntb) tsize <<= 1;
+  Carver cc;
+  const size_t na = (size_t)std::max(n_all, 1), nt = (size_t)std::max(ntb, 1);
+  const size_t o_mean = cc.take(24 * na), o_cov = cc.take(72 * na), o_n = cc.take(4 * na), o_has = cc.take(4 * na);
+  const size_t o_occ = cc.take(4 * na), o_gcell = cc.take(72 * na), o_g2c = cc.take(4 * na);
+  const size_t o_table = cc.take(sizeof(HashEntry) * (size_t)tsize), o_gm = cc.take(8 * nt), o_gb = cc.take(4 * nt);
+  SlabP s_c;
+  if (int rc = slab_alloc(ctx, cc.off, s_c)) return rc;
+  j.n_all = n_all, j.tsize = tsize;
+  j.cmean = (double *)(s_c->p + o_mean), j.ccov = (double *)(s_c->p + o_cov), j.cn = (int *)(s_c->p + o_n);
+  j.chas = (int *)(s_c->p + o_has), j.cocc = (float *)(s_c->p + o_occ), j.gcell = (double *)(s_c->p + o_gcell);
+  j.g2c = (int *)(s_c->p + o_g2c), j.table = (HashEntry *)(s_c->p + o_table);
+  j.gmask_t = (unsigned long long *)(s_c->p + o_gm), j.gbase_t = (int *)(s_c->p + o_gb);
+  CU_TRY(ctx, cudaMemsetAsync(j.table, 0xFF, sizeof(HashEntry) * (size_t)tsize, st));
+  CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, st));
+  ctx->launches += launch_from_cells_place(d_job, d_cells, (int)n, d_vox, st);
+  ctx->launches += launch_gview(d_job, 1, std::max(ntb, 1), st);
+  CU_TRY(ctx, cudaMemcpyAsync(cnts, j.counts, 32, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  m->s_blocks = s_b, m->s_cells = s_c;
+  m->amask = j.amask, m->abase = j.abase, m->tb_list = j.tb_list, m->counts = j.counts;
+  m->n_all = n_all, m->ntb = ntb, m->ng = cnts[2], m->ngb = cnts[3];
+  m->cmean = j.cmean, m->ccov = j.ccov, m->cn = j.cn, m->chas = j.chas, m->cocc = j.cocc;
+  m->gcell = j.gcell, m->g2c = j.g2c, m->table = j.table, m->tsize = tsize;
+  return NDTB_OK;
+}
+
+int ndtb_map_grid(const ndtb_map *m, ndtb_grid *g) {
+  if (!m || !g) return NDTB_ERR_ARG;
+  if (!m->grid_ready) return NDTB_ERR_GRID;
+  for (int i = 0; i < 3; i++) g->center[i] = m->g.center[i], g->cell[i] = m->g.cell[i], g->size[i] = m->g.size[i];
+  return NDTB_OK;
+}
+
+int64_t ndtb_map_num_cells(const ndtb_map *m, int gaussian_only) {
+  if (!m) return NDTB_ERR_ARG;
+  return gaussian_only ? m->ng : m->n_all;
+}
+
+int64_t ndtb_map_export_cells(const ndtb_map *m, ndtb_cell *out, int64_t cap, int gaussian_only) {
+  if (!m || cap < 0 || (cap > 0 && !out)) return NDTB_ERR_ARG;
+  ndtb_ctx *ctx = m->ctx;
+  if (m->n_all == 0) return 0;
+  SlabP tmp;
+  if (int rc = slab_alloc(ctx, sizeof(ndtb_cell) * (size_t)m->n_all + sizeof(BuildJob) + 256, tmp)) return rc;
+  BuildJob j;
+  std::memset(&j, 0, sizeof j);
+  j.g = m->g, j.amask = m->amask, j.abase = m->abase, j.tb_list = m->tb_list, j.counts = m->counts;
+  j.cmean = m->cmean, j.ccov = m->ccov, j.cn = m->cn, j.chas = m->chas, j.cocc = m->cocc;
+  BuildJob *d_job = (BuildJob *)(tmp->p + ((sizeof(ndtb_cell) * (size_t)m->n_all + 255) & ~(size_t)255));
+  CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_export(d_job, m->ntb, (ndtb_cell *)tmp->p, ctx->stream);
+  std::vector<ndtb_cell> h((size_t)m->n_all);
+  CU_TRY(ctx, cudaMemcpyAsync(h.data(), tmp->p, sizeof(ndtb_cell) * (size_t)m->n_all, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<std::pair<int64_t, int>> ord;
+  for (int i = 0; i < m->n_all; i++) {
+    if (gaussian_only && !h[i].has_gaussian) continue;
+    ord.push_back({((int64_t)h[i].idx[0] * m->g.size[1] + h[i].idx[1]) * m->g.size[2] + h[i].idx[2], i});
+  }
+  std::sort(ord.begin(), ord.end());
+  for (size_t k = 0; k < ord.size() && (int64_t)k < cap; k++) out[k] = h[ord[k].second];
+  return (int64_t)ord.size();
+}
+
+int64_t ndtb_map_point_indices(const ndtb_map *m, const float *pts, int64_t n, int mem, int32_t *out) {
+  const bool count_only = mem == NDTB_MEM_DEVICE + 1;  // internal: device points, no index output
+  if (count_only) mem = NDTB_MEM_DEVICE;
+  if (!m || n < 0 || n > 0x7fffffff || (n > 0 && (!pts || (!out && !count_only)))) return NDTB_ERR_ARG;
+  if (!m->grid_ready) return NDTB_ERR_GRID;
+  ndtb_ctx *ctx = m->ctx;
+  if (n == 0) return 0;
+  SlabP pbuf, obuf;
+  const float4 *d_pts = (const float4 *)pts;
+  if (mem != NDTB_MEM_DEVICE) {
+    if (int rc = stage_points(ctx, pts, n, mem, pbuf)) return rc;
+    d_pts = (const float4 *)pbuf->p;
+  }
+  if (int rc = slab_alloc(ctx, 12 * (size_t)n + 256, obuf)) return rc;
+  int *d_nin = (int *)(obuf->p + ((12 * (size_t)n + 255) & ~(size_t)255));
+  int *d_out = (mem == NDTB_MEM_DEVICE && !count_only) ? out : (int *)obuf->p;
+  CU_TRY(ctx, cudaMemsetAsync(d_nin, 0, 4, ctx->stream));
+  ctx->launches += launch_point_indices(m->g, d_pts, (int)n, d_out, d_nin, ctx->stream);
+  int nin = 0;
+  if (mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 12 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(&nin, d_nin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return nin;
+}
+
+// ---- matcher
+int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T, const ndtb_params *p,
+                         int want_hessian, double *out43, int64_t *n_pairs) {
+  if (!ctx || !tgt || !src || !T || !p || !out43) return NDTB_ERR_ARG;
+  if (!map_ok(tgt) || !map_ok(src)) return NDTB_ERR_GRID;
+  if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(tgt))) return rc;
+  if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(src))) return rc;
+  MatchJob j;
+  fill_job(j, tgt, src, T, nullptr);
+  MatchConfig cfg = make_config(ctx, p, 2);
+  const int W = acc_total();
+  int n_ctas = std::max(1, std::min(ctx->sm_count, (src->ng + 255) / 256));
+  SlabP s;
+  if (int rc = slab_alloc(ctx, sizeof(MatchJob) + 256 + 8 * (size_t)W * (n_ctas + 1), s)) return rc;
+  MatchJob *d_job = (MatchJob *)s->p;
+  double *d_part = (double *)(s->p + ((sizeof(MatchJob) + 255) & ~(size_t)255));
+  double *d_out = d_part + (size_t)W * n_ctas;
+  CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, launch_derivatives(d_job, cfg, want_hessian != 0, n_ctas, d_part, d_out, ctx->stream));
+  ctx->launches += 2;
+  std::vector<double> h((size_t)W);
+  CU_TRY(ctx, cudaMemcpyAsync(h.data(), d_out, 8 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  out43[0] = h[0];
+  for (int i = 0; i < 6; i++) out43[1 + i] = h[ACC_G + i];
+  for (int a = 0; a < 6; a++)
+    for (int b = a; b < 6; b++) out43[7 + a * 6 + b] = out43[7 + b * 6 + a] = want_hessian ? h[hidx(a, b)] : 0.0;
+  if (n_pairs) *n_pairs = (int64_t)h[28];
+  return NDTB_OK;
+}
+
+int ndtb_d2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0, const ndtb_params *p,
+                   ndtb_result *res) {
+  if (!ctx || !tgt || !src || !T0 || !p || !res) return NDTB_ERR_ARG;
+  return match_batch_impl(ctx, 1, &tgt, &src, T0, nullptr, p, 0, NDTB_MEM_HOST, res, nullptr);
+}
+
+int ndtb_fusion_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0, const double *Tcov36,
+                      const ndtb_params *p, ndtb_result *res) {
+  if (!ctx || !tgt || !src || !T0 || !Tcov36 || !p || !res) return NDTB_ERR_ARG;
+  double Q[36];
+  if (!inv6(Tcov36, Q)) return NDTB_ERR_SINGULAR;
+  return match_batch_impl(ctx, 1, &tgt, &src, T0, Q, p, 0, NDTB_MEM_HOST, res, nullptr);
+}
+
+int ndtb_d2d_match_batch(ndtb_ctx *ctx, int64_t n_edges, const ndtb_map *const *tgt, const ndtb_map *const *src,
+                         const double *T0s, const ndtb_params *p, int with_covariance, int out_mem, ndtb_result *res,
+                         double *cov36s) {
+  if (!ctx || n_edges < 0 || (n_edges > 0 && (!tgt || !src || !T0s || !res)) || !p) return NDTB_ERR_ARG;
+  return match_batch_impl(ctx, n_edges, tgt, src, T0s, nullptr, p, with_covariance && cov36s, out_mem, res, cov36s);
+}
+
+int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T, const ndtb_params *p,
+                        double *cov36) {
+  if (!ctx || !tgt || !src || !T || !p || !cov36) return NDTB_ERR_ARG;
+  if (!map_ok(tgt) || !map_ok(src)) return NDTB_ERR_GRID;
+  if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(tgt))) return rc;
+  if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(src))) return rc;
+  cudaStream_t st = ctx->stream;
+  MatchJob j;
+  fill_job(j, tgt, src, T, nullptr);
+  MatchConfig cfg = make_config(ctx, p, 2);
+  const int n_chunks = std::max(1, std::min(ctx->sm_count, (src->ng + 127) / 128));
+  Carver c;
+  const size_t o_job = c.take(sizeof j), o_goff = c.take(8), o_gt = c.take(48 * (size_t)std::max(tgt->ng, 1));
+  const size_t o_part = c.take(8 * (size_t)cov_partial_width() * n_chunks), o_cov = c.take(288), o_stat = c.take(4);
+  SlabP s;
+  if (int rc = slab_alloc(ctx, c.off, s)) return rc;
+  CU_TRY(ctx, cudaMemsetAsync(s->p, 0, s->bytes, st));
+  CU_TRY(ctx, cudaMemcpyAsync(s->p + o_job, &j, sizeof j, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, launch_covariance((MatchJob *)(s->p + o_job), 1, cfg, nullptr, (const long long *)(s->p + o_goff),
+                                (double *)(s->p + o_gt), (double *)(s->p + o_part), n_chunks, (double *)(s->p + o_cov),
+                                (int *)(s->p + o_stat), st));
+  ctx->launches += 2;
+  int status = 0;
+  CU_TRY(ctx, cudaMemcpyAsync(cov36, s->p + o_cov, 288, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaMemcpyAsync(&status, s->p + o_stat, 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  return status;
+}
+
+int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_pts, const int64_t *n_tgt,
+                        const float *const *src_pts, const int64_t *n_src, const double *T0s, double cell,
+                        const double *map_size, double range_limit, const ndtb_params *p, int with_covariance, int in_mem,
+                        int out_mem, ndtb_result *res, double *cov36s) {
+  if (!ctx || n_pairs < 0 || !p || !(cell > 0)) return NDTB_ERR_ARG;
+  if (n_pairs == 0) return NDTB_OK;
+  if (!tgt_pts || !n_tgt || !src_pts || !n_src || !T0s || !res) return NDTB_ERR_ARG;
+  std::vector<std::unique_ptr<ndtb_map>> own((size_t)(2 * n_pairs));
+  std::vector<ndtb_map *> maps((size_t)(2 * n_pairs));
+  std::vector<const float *> pts((size_t)(2 * n_pairs));
+  std::vector<int64_t> npts((size_t)(2 * n_pairs));
+  for (int64_t i = 0; i < 2 * n_pairs; i++) {
+    own[i].reset(new ndtb_map());
+    ndtb_map *m = own[i].get();
+    m->ctx = ctx;
+    m->cell[0] = m->cell[1] = m->cell[2] = cell;
+    std::memset(&m->g, 0, sizeof m->g);
+    if (map_size && map_size[0] > 0 && map_size[1] > 0 && map_size[2] > 0)
+      m->map_sizex = (float)map_size[0], m->map_sizey = (float)map_size[1], m->map_sizez = (float)map_size[2];
+    maps[i] = m;
+    const int64_t e = i >> 1;
+    pts[i] = (i & 1) ? src_pts[e] : tgt_pts[e];
+    npts[i] = (i & 1) ? n_src[e] : n_tgt[e];
+  }
+  if (int rc = ndtb_map_build_batch(ctx, 2 * n_pairs, maps.data(), pts.data(), npts.data(), range_limit, in_mem, 0xffffffffu, 255.f))
+    return rc;
+  std::vector<const ndtb_map *> tg((size_t)n_pairs), sr((size_t)n_pairs);
+  for (int64_t e = 0; e < n_pairs; e++) {
+    tg[e] = maps[2 * e], sr[e] = maps[2 * e + 1];
+    if (!maps[2 * e]->grid_ready || !maps[2 * e + 1]->grid_ready) return NDTB_ERR_EMPTY;
+  }
+  const int rc = match_batch_impl(ctx, n_pairs, tg.data(), sr.data(), T0s, nullptr, p, with_covariance && cov36s, out_mem, res, cov36s);
+  if (rc == NDTB_OK && out_mem == NDTB_MEM_DEVICE) {
+    // outputs stay on the device and the temporary maps are released stream-ordered: no host sync needed
+  }
+  return rc;
+}
+
+int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T, double *score) {
+  if (!ctx || !ref || !mov || !T || !score) return NDTB_ERR_ARG;
+  if (!map_ok(ref) || !map_ok(mov)) return NDTB_ERR_GRID;
+  if (mov->n_all == 0 || ref->n_all == 0) {
+    *score = 1.0;
+    return NDTB_OK;
+  }
+  BuildJob j[2];
+  std::memset(j, 0, sizeof j);
+  const ndtb_map *mm[2] = {ref, mov};
+  for (int i = 0; i < 2; i++) {
+    j[i].g = mm[i]->g, j[i].amask = mm[i]->amask, j[i].abase = mm[i]->abase, j[i].tb_list = mm[i]->tb_list;
+    j[i].counts = mm[i]->counts, j[i].cocc = mm[i]->cocc;
+  }
+  Carver c;
+  const size_t o_j = c.take(sizeof j), o_T = c.take(128), o_out = c.take(8);
+  SlabP s;
+  if (int rc = slab_alloc(ctx, c.off, s)) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(s->p + o_j, j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(s->p + o_T, T, 128, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_overlap((const BuildJob *)(s->p + o_j), (const double *)(s->p + o_T), (double *)(s->p + o_out), ctx->stream);
+  CU_TRY(ctx, cudaMemcpyAsync(score, s->p + o_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NDTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,585 @@
+// d2d.cu — kernel (ii): NDT-D2D score / gradient / Hessian accumulation, the device-resident Newton +
+// More-Thuente loop around it, and the covariance pass.
+//
+// Reference path replaced:
+//   a9  NDTMatcherD2D::derivativesNDT [upstream]   called at ndt_feature/include/ndt_feature/ndt_matcher_d2d_fusion.h:856,617,444
+//   a14 NDTMap::pseudoTransformNDT / per-iteration cell move (fusion.h:840, :1047-1056) — fused: every pass
+//       applies the current pose to the immutable source cells on the fly, nothing is written back
+//   a15 LazyGrid::getClosestNDTCells [upstream] — (2k+1)^3 cube probe, done per 4x4x4 block (8 hash probes for k=2)
+//   a8/a5 NDTMatcherD2D::match / matchFusion (fusion.h:797-1155) — optimizer.h state machine, one thread
+//   a11 NDTMatcherD2D::covariance [upstream] (ndt_feature_graph.cpp:298)
+//
+// Work decomposition of one derivative pass: a warp takes 32 source cells per round (one per lane): each lane
+// moves its cell, stages (mu, C) in shared memory, probes the target's block table and pushes its hits
+// (source lane, target slot) into a per-warp queue; the queue is drained 32 pairs at a time, ONE PAIR PER LANE,
+// so the fp64 pair arithmetic always runs on full warps although hit counts per source cell vary from 0 to 125.
+// All reductions use fixed trees (shuffle butterflies, ordered partial sums): results are run-to-run deterministic.
+#include <cooperative_groups.h>
+
+#include "../../include/ndtb.h"
+#include "engine.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ndtb {
+
+constexpr int MATCH_THREADS = 256;
+constexpr int MATCH_WARPS = MATCH_THREADS / 32;
+constexpr int QCAP = 128;       // per-warp pair queue capacity (entries); >= 64
+constexpr int ACC_PAIRS = 28;   // slot counting contributing pairs
+constexpr int ACC_TOTAL = 29;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct WarpScratch {
+  double stage[GC][32];  // moved source cells of the current round, SoA: stage[k][lane]
+  unsigned queue[QCAP];  // (source lane << 27) | target slot
+};
+
+struct PassCtx {
+  const GridDesc *g;  // target grid (shared memory)
+  const HashEntry *table;
+  int tsize;
+  const double *tcell;
+  const double *scell;
+  int ns;
+  int k;
+  double lfd1, lfd2;
+};
+
+__device__ __forceinline__ bool table_find(const HashEntry *table, int tsize, int key, int &base,
+                                           unsigned long long &mask) {
+  unsigned h = hash_block(key, tsize);
+#pragma unroll 1
+  for (;;) {
+    const int4 e = *reinterpret_cast<const int4 *>(table + h);
+    if (e.x == key) {
+      base = e.y;
+      mask = ((unsigned long long)(unsigned)e.w << 32) | (unsigned)e.z;
+      return true;
+    }
+    if (e.x == -1) return false;
+    h = (h + 1) & (unsigned)(tsize - 1);
+  }
+}
+
+// 4-bit mask of local coordinates [lo,hi] of block b (4 voxels) clipped to the probe range [c-k, c+k]
+__device__ __forceinline__ unsigned axis_bits(int c, int k, int b) {
+  int lo = c - k - 4 * b, hi = c + k - 4 * b;
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > 3 ? 3 : hi;
+  return ((2u << hi) - 1u) & ~((1u << lo) - 1u);
+}
+__device__ __forceinline__ unsigned long long expand_x(unsigned a) {
+  return ((a & 1u) ? 0xFFFFull : 0ull) | ((a & 2u) ? 0xFFFFull << 16 : 0ull) | ((a & 4u) ? 0xFFFFull << 32 : 0ull) |
+         ((a & 8u) ? 0xFFFFull << 48 : 0ull);
+}
+__device__ __forceinline__ unsigned long long expand_y(unsigned a) {
+  const unsigned long long row = ((a & 1u) ? 0xFull : 0ull) | ((a & 2u) ? 0xF0ull : 0ull) | ((a & 4u) ? 0xF00ull : 0ull) |
+                                 ((a & 8u) ? 0xF000ull : 0ull);
+  return row * 0x0001000100010001ull;
+}
+__device__ __forceinline__ unsigned long long expand_z(unsigned a) { return (unsigned long long)a * 0x1111111111111111ull; }
+
+template <bool HESS>
+__device__ __forceinline__ void process_entry(const PassCtx &c, const WarpScratch &ws, unsigned e, double *acc) {
+  const int sl = e >> 27;
+  const int slot = e & 0x7FFFFFF;
+  double C[6], m[3], S[6];
+  const double mu0 = ws.stage[0][sl], mu1 = ws.stage[1][sl], mu2 = ws.stage[2][sl];
+#pragma unroll
+  for (int j = 0; j < 6; j++) C[j] = ws.stage[3 + j][sl];
+  const double *t = c.tcell + (size_t)slot * GC;
+#pragma unroll
+  for (int j = 0; j < 3; j++) m[j] = __ldg(t + j);
+#pragma unroll
+  for (int j = 0; j < 6; j++) S[j] = __ldg(t + 3 + j);
+  if (pair_contrib<HESS>(mu0, mu1, mu2, C, m, S, c.lfd1, c.lfd2, acc, nullptr)) acc[ACC_PAIRS] += 1.0;
+}
+
+// moved source cell: mean <- R mean + t (bit-exact operation order of the CPU restatement, the voxel of the
+// moved mean selects the neighbourhood), cov <- R cov R^T
+__device__ __forceinline__ void move_cell(const double *P, const double *s, double *mu, double *C) {
+  const double m0 = s[0], m1 = s[1], m2 = s[2];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    mu[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[r * 3], m0), __dmul_rn(P[r * 3 + 1], m1)), __dmul_rn(P[r * 3 + 2], m2)),
+                      P[9 + r]);
+  const double s00 = s[3], s01 = s[4], s02 = s[5], s11 = s[6], s12 = s[7], s22 = s[8];
+  double A[9];  // A = R * Sigma
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const double r0 = P[r * 3], r1 = P[r * 3 + 1], r2 = P[r * 3 + 2];
+    A[r * 3 + 0] = r0 * s00 + r1 * s01 + r2 * s02;
+    A[r * 3 + 1] = r0 * s01 + r1 * s11 + r2 * s12;
+    A[r * 3 + 2] = r0 * s02 + r1 * s12 + r2 * s22;
+  }
+  C[0] = A[0] * P[0] + A[1] * P[1] + A[2] * P[2];
+  C[1] = A[0] * P[3] + A[1] * P[4] + A[2] * P[5];
+  C[2] = A[0] * P[6] + A[1] * P[7] + A[2] * P[8];
+  C[3] = A[3] * P[3] + A[4] * P[4] + A[5] * P[5];
+  C[4] = A[3] * P[6] + A[4] * P[7] + A[5] * P[8];
+  C[5] = A[6] * P[6] + A[7] * P[7] + A[8] * P[8];
+}
+
+// One derivative pass over the source cells assigned to this warp (rounds wg, wg+nwg, ...).
+template <bool HESS>
+__device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int wg, int nwg, double *acc) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int k = c.k;
+  const int span = (2 * k + 3) / 4 + 1;  // max 4-blocks touched by 2k+1 consecutive voxels
+  const int nb0 = c.g->nb[0], nb1 = c.g->nb[1], nb2 = c.g->nb[2];
+  int qcount = 0;
+  for (int base = wg * 32; base < c.ns; base += nwg * 32) {
+    const int i = base + lane;
+    bool valid = i < c.ns;
+    int ix = 0, iy = 0, iz = 0;
+    if (valid) {
+      double mu[3], C[6];
+      move_cell(P, c.scell + (size_t)i * GC, mu, C);
+      // pcl::PointXYZ is float: the lookup point is the float-rounded mean
+      valid = voxel_index(*c.g, (double)__double2float_rn(mu[0]), (double)__double2float_rn(mu[1]),
+                          (double)__double2float_rn(mu[2]), ix, iy, iz);
+#pragma unroll
+      for (int j = 0; j < 3; j++) ws.stage[j][lane] = mu[j];
+#pragma unroll
+      for (int j = 0; j < 6; j++) ws.stage[3 + j][lane] = C[j];
+    }
+    __syncwarp();
+    const int bx0 = (ix - k) >> 2, by0 = (iy - k) >> 2, bz0 = (iz - k) >> 2;
+    const int bx1 = (ix + k) >> 2, by1 = (iy + k) >> 2, bz1 = (iz + k) >> 2;
+    for (int dx = 0; dx < span; dx++) {
+      const int bx = bx0 + dx;
+      const bool okx = valid && bx <= bx1 && bx >= 0 && bx < nb0;
+      const unsigned long long mx = expand_x(axis_bits(ix, k, bx));
+      for (int dy = 0; dy < span; dy++) {
+        const int by = by0 + dy;
+        const bool oky = okx && by <= by1 && by >= 0 && by < nb1;
+        const unsigned long long mxy = mx & expand_y(axis_bits(iy, k, by));
+        for (int dz = 0; dz < span; dz++) {
+          const int bz = bz0 + dz;
+          unsigned long long hits = 0, bmask = 0;
+          int cbase = 0;
+          if (oky && bz <= bz1 && bz >= 0 && bz < nb2) {
+            if (table_find(c.table, c.tsize, (bx * nb1 + by) * nb2 + bz, cbase, bmask))
+              hits = bmask & mxy & expand_z(axis_bits(iz, k, bz));
+          }
+          // push this probe's hits, one per lane per iteration
+          for (;;) {
+            const unsigned active = __ballot_sync(FULL, hits != 0ull);
+            if (!active) break;
+            if (qcount + 32 > QCAP) {
+              __syncwarp();
+              while (qcount >= 32) {
+                qcount -= 32;
+                process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
+              }
+              __syncwarp();
+            }
+            if (hits) {
+              const int b = __ffsll((long long)hits) - 1;
+              hits &= hits - 1ull;
+              const int slot = cbase + __popcll(bmask & ((1ull << b) - 1ull));
+              ws.queue[qcount + __popc(active & lt)] = ((unsigned)lane << 27) | (unsigned)slot;
+            }
+            qcount += __popc(active);
+          }
+        }
+      }
+    }
+    // end of round: the staged cells are about to be overwritten — drain everything
+    __syncwarp();
+    while (qcount >= 32) {
+      qcount -= 32;
+      process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
+    }
+    if (qcount > 0) {
+      if (lane < qcount) process_entry<HESS>(c, ws, ws.queue[lane], acc);
+      qcount = 0;
+    }
+    __syncwarp();
+  }
+}
+
+// deterministic block reduction of n per-thread accumulators -> sums[n] (shared)
+__device__ __forceinline__ void block_reduce(const double *acc, int n, double *red, double *sums, int nwarps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < ACC_TOTAL; j++) {
+    if (j < n || j == ACC_PAIRS) {
+      double v = acc[j];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+      if (lane == 0) red[warp * ACC_TOTAL + j] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < ACC_TOTAL) {
+    double s = 0.0;
+    if (threadIdx.x < n || threadIdx.x == ACC_PAIRS)
+      for (int w = 0; w < nwarps; w++) s += red[w * ACC_TOTAL + threadIdx.x];
+    sums[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ TMA bulk copy of the block table
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_table_bulk(HashEntry *dst, const HashEntry *src, int entries, uint64_t *mbar) {
+  const unsigned bar = smem_u32(mbar);
+  const unsigned bytes = (unsigned)entries * (unsigned)sizeof(HashEntry);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    const unsigned chunk = 16384u;
+    for (unsigned off = 0; off < bytes; off += chunk) {
+      const unsigned n = bytes - off < chunk ? bytes - off : chunk;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(reinterpret_cast<const char *>(dst) + off)),
+          "l"(reinterpret_cast<const char *>(src) + off), "r"(n), "r"(bar)
+          : "memory");
+    }
+  }
+  // every thread waits for phase 0 of the barrier
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar)
+        : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ K5: whole registration in one launch
+struct MatchShared {
+  OptState st;
+  OptParams prm;
+  GridDesc grid;
+  double P[12];  // pose of the pending evaluation: R row-major, t
+  double sums[ACC_TOTAL];
+  double red[MATCH_WARPS * ACC_TOTAL];
+  double pairs_last;
+  uint64_t mbar;
+};
+
+extern __shared__ __align__(16) unsigned char dyn_smem[];
+
+__global__ void __launch_bounds__(MATCH_THREADS, 1)
+match_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, ndtb_result *__restrict__ out) {
+  // dynamic smem: [table staging][MatchShared][WarpScratch x warps]
+  HashEntry *stab = reinterpret_cast<HashEntry *>(dyn_smem);
+  MatchShared &sh = *reinterpret_cast<MatchShared *>(dyn_smem + (size_t)cfg.table_smem_entries * sizeof(HashEntry));
+  WarpScratch *wsp = reinterpret_cast<WarpScratch *>(reinterpret_cast<unsigned char *>(&sh) + ((sizeof(MatchShared) + 15) & ~(size_t)15));
+  const MatchJob &job = jobs[blockIdx.x];
+  const int warp = threadIdx.x >> 5;
+
+  PassCtx c;
+  c.g = &sh.grid;
+  c.tsize = job.tgt.tsize;
+  c.tcell = job.tgt.gcell;
+  c.scell = job.src_gcell;
+  c.ns = job.src_ng;
+  c.k = cfg.n_neighbours;
+  c.lfd1 = cfg.lfd1, c.lfd2 = cfg.lfd2;
+  const bool staged = job.tgt.tsize <= cfg.table_smem_entries;
+  c.table = staged ? stab : job.tgt.table;
+
+  if (threadIdx.x == 0) {
+    sh.grid = job.tgt.g;
+    OptParams &p = sh.prm;
+    p.itr_max = cfg.itr_max, p.step_control = cfg.step_control, p.regularize = cfg.regularize;
+    p.fusion = job.fusion, p.soft = job.fusion && cfg.soft, p.tik = job.fusion && cfg.tik;
+    p.delta_score = cfg.delta_score;
+    for (int i = 0; i < 36; i++) p.Q[i] = job.Q[i];
+    opt_begin(sh.st, p, job.T0);
+    for (int i = 0; i < 9; i++) sh.P[i] = sh.st.Peval.R[i];
+    for (int i = 0; i < 3; i++) sh.P[9 + i] = sh.st.Peval.t[i];
+  }
+  if (staged)
+    stage_table_bulk(stab, job.tgt.table, job.tgt.tsize, &sh.mbar);
+  __syncthreads();
+
+  for (;;) {
+    if (sh.st.phase == PH_DONE) break;  // uniform: shared state, read after a barrier
+    const bool hess = sh.st.want_hess != 0;
+    double acc[ACC_TOTAL];
+#pragma unroll
+    for (int j = 0; j < ACC_TOTAL; j++) acc[j] = 0.0;
+    if (hess)
+      d2d_pass<true>(c, sh.P, wsp[warp], warp, MATCH_WARPS, acc);
+    else
+      d2d_pass<false>(c, sh.P, wsp[warp], warp, MATCH_WARPS, acc);
+    block_reduce(acc, hess ? 28 : 7, sh.red, sh.sums, MATCH_WARPS);
+    if (threadIdx.x == 0) {
+      opt_advance(sh.st, sh.prm, sh.sums);
+      for (int i = 0; i < 9; i++) sh.P[i] = sh.st.Peval.R[i];
+      for (int i = 0; i < 3; i++) sh.P[9 + i] = sh.st.Peval.t[i];
+    }
+    __syncthreads();
+  }
+
+  if (threadIdx.x == 0) {
+    const OptState &s = sh.st;
+    ndtb_result r;
+    pose_to_cm(s.T, r.T);
+    r.score = s.score_here, r.score_best = s.score_best;
+    r.converged = s.ret, r.iterations = s.itr, r.n_hess_passes = s.n_hess, r.n_grad_passes = s.n_grad;
+    r.exit_code = s.exit_code;
+    int changed = 0;
+    for (int i = 0; i < 16; i++) changed |= (r.T[i] != job.T0[i]);
+    r.pose_changed = changed;
+    r.status = (s.ret ? NDTB_ST_CONVERGED : NDTB_ST_ITR_MAX) | (changed ? NDTB_ST_POSE_CHANGED : 0) |
+               (s.nonfinite ? NDTB_ST_NONFINITE : 0) | ((job.src_ng == 0 || job.tgt.ng == 0) ? NDTB_ST_NO_CELLS : 0);
+    r.n_src_cells = job.src_ng, r.n_tgt_cells = job.tgt.ng, r.tgt_table_entries = job.tgt.tsize;
+    out[blockIdx.x] = r;
+  }
+}
+
+size_t match_smem_bytes(int table_entries) {
+  return (size_t)table_entries * sizeof(HashEntry) + ((sizeof(MatchShared) + 15) & ~(size_t)15) +
+         MATCH_WARPS * sizeof(WarpScratch);
+}
+
+cudaError_t launch_match(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, ndtb_result *d_out,
+                         cudaStream_t stream) {
+  const size_t smem = match_smem_bytes(cfg.table_smem_entries);
+  cudaError_t e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  match_kernel<<<n_jobs, MATCH_THREADS, smem, stream>>>(d_jobs, cfg, d_out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ stand-alone derivativesNDT (API + tests)
+struct DerivShared {
+  GridDesc grid;
+  double P[12];
+  double sums[ACC_TOTAL];
+  double red[MATCH_WARPS * ACC_TOTAL];
+};
+
+template <bool HESS>
+__global__ void __launch_bounds__(MATCH_THREADS, 1)
+deriv_kernel(const MatchJob *__restrict__ job_p, MatchConfig cfg, double *__restrict__ partial /*[grid][ACC_TOTAL]*/) {
+  __shared__ DerivShared sh;
+  __shared__ WarpScratch ws[MATCH_WARPS];
+  const MatchJob &job = *job_p;
+  if (threadIdx.x == 0) {
+    sh.grid = job.tgt.g;
+    const Pose T = pose_from_cm(job.T0);
+    for (int i = 0; i < 9; i++) sh.P[i] = T.R[i];
+    for (int i = 0; i < 3; i++) sh.P[9 + i] = T.t[i];
+  }
+  __syncthreads();
+  PassCtx c;
+  c.g = &sh.grid;
+  c.table = job.tgt.table, c.tsize = job.tgt.tsize, c.tcell = job.tgt.gcell;
+  c.scell = job.src_gcell, c.ns = job.src_ng;
+  c.k = cfg.n_neighbours, c.lfd1 = cfg.lfd1, c.lfd2 = cfg.lfd2;
+  double acc[ACC_TOTAL];
+#pragma unroll
+  for (int j = 0; j < ACC_TOTAL; j++) acc[j] = 0.0;
+  const int warp = threadIdx.x >> 5;
+  d2d_pass<HESS>(c, sh.P, ws[warp], blockIdx.x * MATCH_WARPS + warp, gridDim.x * MATCH_WARPS, acc);
+  block_reduce(acc, HESS ? 28 : 7, sh.red, sh.sums, MATCH_WARPS);
+  if (threadIdx.x < ACC_TOTAL) partial[blockIdx.x * ACC_TOTAL + threadIdx.x] = sh.sums[threadIdx.x];
+}
+
+__global__ void sum_partials_kernel(const double *__restrict__ partial, int n_parts, int width, double *__restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= width) return;
+  double s = 0.0;
+  for (int p = 0; p < n_parts; p++) s += partial[p * width + j];
+  out[j] = s;
+}
+
+cudaError_t launch_derivatives(const MatchJob *d_job, const MatchConfig &cfg, bool hess, int n_ctas, double *d_partial,
+                               double *d_out29, cudaStream_t stream) {
+  if (hess)
+    deriv_kernel<true><<<n_ctas, MATCH_THREADS, 0, stream>>>(d_job, cfg, d_partial);
+  else
+    deriv_kernel<false><<<n_ctas, MATCH_THREADS, 0, stream>>>(d_job, cfg, d_partial);
+  sum_partials_kernel<<<1, 32, 0, stream>>>(d_partial, n_ctas, ACC_TOTAL, d_out29);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ covariance
+// Definition (fixed by the CPU restatement): H = Hessian at T; rows = per-source-cell gradient
+// sums g_i and per-target-cell gradient sums g_t; cov = H^-1 (sigma^2 sum_c g_c g_c^T) H^-1, sigma = 0.03.
+constexpr int COV_THREADS = 128;
+constexpr int COV_W = 28 + 21;  // H pass sums + upper triangle of sum g g^T
+
+__device__ __forceinline__ void outer_upper(const double *g, double *o) {
+  int n = 0;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) o[n++] += g[a] * g[b];
+}
+
+// grid (chunks, jobs): thread per source cell, hits processed serially; per-target sums by fp64 atomics.
+__global__ void __launch_bounds__(COV_THREADS)
+cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_result *__restrict__ res,
+                const long long *__restrict__ gt_off, double *__restrict__ gt, double *__restrict__ partial) {
+  const MatchJob &job = jobs[blockIdx.y];
+  __shared__ double P[12];
+  __shared__ GridDesc grid;
+  __shared__ double red[(COV_THREADS / 32) * COV_W];
+  const bool skip = res && !res[blockIdx.y].pose_changed;
+  if (threadIdx.x == 0) {
+    grid = job.tgt.g;
+    const Pose T = pose_from_cm(res ? res[blockIdx.y].T : job.T0);
+    for (int i = 0; i < 9; i++) P[i] = T.R[i];
+    for (int i = 0; i < 3; i++) P[9 + i] = T.t[i];
+  }
+  __syncthreads();
+  double acc[COV_W];
+#pragma unroll
+  for (int j = 0; j < COV_W; j++) acc[j] = 0.0;
+  const int k = cfg.n_neighbours;
+  double *gtj = gt + gt_off[blockIdx.y] * 6;
+  if (!skip) {
+    for (int i = blockIdx.x * COV_THREADS + threadIdx.x; i < job.src_ng; i += gridDim.x * COV_THREADS) {
+      double mu[3], C[6], gs[6] = {0, 0, 0, 0, 0, 0};
+      move_cell(P, job.src_gcell + (size_t)i * GC, mu, C);
+      int ix, iy, iz;
+      if (!voxel_index(grid, (double)__double2float_rn(mu[0]), (double)__double2float_rn(mu[1]),
+                       (double)__double2float_rn(mu[2]), ix, iy, iz))
+        continue;
+      for (int bx = (ix - k) >> 2; bx <= (ix + k) >> 2; bx++) {
+        if (bx < 0 || bx >= grid.nb[0]) continue;
+        const unsigned long long mx = expand_x(axis_bits(ix, k, bx));
+        for (int by = (iy - k) >> 2; by <= (iy + k) >> 2; by++) {
+          if (by < 0 || by >= grid.nb[1]) continue;
+          const unsigned long long mxy = mx & expand_y(axis_bits(iy, k, by));
+          for (int bz = (iz - k) >> 2; bz <= (iz + k) >> 2; bz++) {
+            if (bz < 0 || bz >= grid.nb[2]) continue;
+            int cbase;
+            unsigned long long bmask;
+            if (!table_find(job.tgt.table, job.tgt.tsize, (bx * grid.nb[1] + by) * grid.nb[2] + bz, cbase, bmask)) continue;
+            unsigned long long hits = bmask & mxy & expand_z(axis_bits(iz, k, bz));
+            while (hits) {
+              const int b = __ffsll((long long)hits) - 1;
+              hits &= hits - 1ull;
+              const int slot = cbase + __popcll(bmask & ((1ull << b) - 1ull));
+              const double *t = job.tgt.gcell + (size_t)slot * GC;
+              double m[3] = {__ldg(t), __ldg(t + 1), __ldg(t + 2)};
+              double S[6] = {__ldg(t + 3), __ldg(t + 4), __ldg(t + 5), __ldg(t + 6), __ldg(t + 7), __ldg(t + 8)};
+              double g6[6];
+              if (pair_contrib<true>(mu[0], mu[1], mu[2], C, m, S, cfg.lfd1, cfg.lfd2, acc, g6)) {
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                  gs[a] += g6[a];
+                  atomicAdd(gtj + (size_t)slot * 6 + a, g6[a]);
+                }
+              }
+            }
+          }
+        }
+      }
+      outer_upper(gs, acc + 28);
+    }
+  }
+  // block reduce COV_W values (fixed tree) -> partial[job][cta][COV_W]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < COV_W; j++) {
+    double v = acc[j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    if (lane == 0) red[warp * COV_W + j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < COV_W) {
+    double s = 0.0;
+    for (int w = 0; w < COV_THREADS / 32; w++) s += red[w * COV_W + threadIdx.x];
+    partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * COV_W + threadIdx.x] = s;
+  }
+}
+
+// one CTA per job: ordered sum of the partials, sum over target rows, 6x6 sandwich
+__global__ void __launch_bounds__(COV_THREADS)
+cov_finalize_kernel(const MatchJob *__restrict__ jobs, const ndtb_result *__restrict__ res, const long long *__restrict__ gt_off,
+                    const double *__restrict__ gt, const double *__restrict__ partial, int n_chunks,
+                    double *__restrict__ cov36, int *__restrict__ status) {
+  const MatchJob &job = jobs[blockIdx.x];
+  __shared__ double tot[COV_W];
+  __shared__ double red[(COV_THREADS / 32) * 21];
+  double *out = cov36 + (size_t)blockIdx.x * 36;
+  if (res && !res[blockIdx.x].pose_changed) {  // ndt_feature_graph.cpp:300-310
+    if (threadIdx.x < 36) out[threadIdx.x] = (threadIdx.x % 7 == 0) ? 0.02 : 0.0;
+    if (threadIdx.x == 0 && status) status[blockIdx.x] = 0;
+    return;
+  }
+  if (threadIdx.x < COV_W) {
+    double s = 0.0;
+    for (int p = 0; p < n_chunks; p++) s += partial[((size_t)blockIdx.x * n_chunks + p) * COV_W + threadIdx.x];
+    tot[threadIdx.x] = s;
+  }
+  double o[21];
+#pragma unroll
+  for (int j = 0; j < 21; j++) o[j] = 0.0;
+  const double *gtj = gt + gt_off[blockIdx.x] * 6;
+  for (int t = threadIdx.x; t < job.tgt.ng; t += COV_THREADS) {
+    double g[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) g[a] = gtj[(size_t)t * 6 + a];
+    outer_upper(g, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 21; j++) {
+    double v = o[j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    if (lane == 0) red[warp * 21 + j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double H[36], JtJ[36], Hinv[36], tmp[36];
+    int n = 0;
+    for (int a = 0; a < 6; a++)
+      for (int b = a; b < 6; b++, n++) {
+        H[a * 6 + b] = H[b * 6 + a] = tot[ACC_H + n];
+        double s = tot[28 + n];
+        for (int w = 0; w < COV_THREADS / 32; w++) s += red[w * 21 + n];
+        JtJ[a * 6 + b] = JtJ[b * 6 + a] = s;
+      }
+    const bool ok = inv6(H, Hinv);
+    const double sigmaS = 0.03 * 0.03;
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++) {
+        double s = 0;
+        for (int q = 0; q < 6; q++) s += Hinv[i * 6 + q] * sigmaS * JtJ[q * 6 + j];
+        tmp[i * 6 + j] = s;
+      }
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++) {
+        double s = 0;
+        for (int q = 0; q < 6; q++) s += tmp[i * 6 + q] * Hinv[q * 6 + j];
+        out[i * 6 + j] = ok ? s : 0.0;
+      }
+    if (status) status[blockIdx.x] = ok ? 0 : NDTB_ERR_SINGULAR;
+  }
+}
+
+cudaError_t launch_covariance(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, const ndtb_result *d_res,
+                              const long long *d_gt_off, double *d_gt, double *d_partial, int n_chunks,
+                              double *d_cov36, int *d_status, cudaStream_t stream) {
+  dim3 grid(n_chunks, n_jobs);
+  cov_pass_kernel<<<grid, COV_THREADS, 0, stream>>>(d_jobs, cfg, d_res, d_gt_off, d_gt, d_partial);
+  cov_finalize_kernel<<<n_jobs, COV_THREADS, 0, stream>>>(d_jobs, d_res, d_gt_off, d_gt, d_partial, n_chunks, d_cov36,
+                                                         d_status);
+  return cudaGetLastError();
+}
+
+int cov_partial_width() { return COV_W; }
+int acc_total() { return ACC_TOTAL; }
+
+}  // namespace ndtb

@@ -1,0 +1,570 @@
+// map_build.cu — kernel (i): voxel binning of a scan and per-voxel mean / covariance (NDT cell) computation,
+// batched over many maps per launch.  COMPILED WITH -fmad=false: every floating-point operation below is a
+// separately rounded IEEE operation, in the same order as the CPU restatement, so voxel indices, N, means,
+// covariances and eigen-clamped covariances are BIT-IDENTICAL to it (exact-parity claim of DESIGN.md).
+//
+// Reference path replaced:
+//   a12 NDTMap::loadPointCloud / addPointCloud end-point binning + LazyGrid::getIndexForPoint/addPoint [upstream]
+//       call sites ndt_feature/src/ndt_feature_src/ndt_feature_fuser_hmt.cpp:92,201-225,485
+//   a13 NDTMap::computeNDTCells -> NDTCell::computeGaussian(SAMPLE_VARIANCE) + rescaleCovariance [upstream]
+//       call sites ndt_feature_fuser_hmt.cpp:94,227,486
+//
+// Pipeline (all order-independent pieces are parallel; the order-dependent sums are done in point-index order):
+//   centroid/extent (guess-size grids only) -> mark touched voxels in a 1-bit-per-voxel block mask ->
+//   popcount scan (cell numbering = (block, bit) order, touched-block list) -> per-cell counts -> segment scan ->
+//   scatter point ids -> per cell: rank-sort ids, sequential mean, sequential scatter matrix, merge with the
+//   previous (N, mean, cov), occupancy, 3x3 Jacobi eigen clamp -> Gaussian view (compact cells + block hash table).
+#include "map_build.cuh"
+
+namespace ndtb {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ bool pt_skip(const float4 p, double range_limit) {
+  if (isnan(p.x) || isnan(p.y) || isnan(p.z)) return true;
+  if (range_limit > 0) {
+    const double d = sqrt((double)p.x * (double)p.x + (double)p.y * (double)p.y + (double)p.z * (double)p.z);
+    if (d > range_limit) return true;
+  }
+  return false;
+}
+
+// ---- guess-size grids: centroid in point order (one warp per map), then extents -------------------------
+// out[map*8 + {0,1,2}] = centroid sum / count, [3] = count, [4] = maxDist bits, [5] = max dz key, [6] = min dz key
+__global__ void k_centroid(const BuildJob *__restrict__ jobs, const int *__restrict__ which, double *__restrict__ out) {
+  const BuildJob &j = jobs[which[blockIdx.x]];
+  const int lane = threadIdx.x;
+  double sx = 0, sy = 0, sz = 0;
+  long long cnt = 0;
+  for (int base = 0; base < j.npts; base += 32) {
+    const int i = base + lane;
+    float4 p = make_float4(0, 0, 0, 0);
+    bool use = false;
+    if (i < j.npts) {
+      p = j.pts[i];
+      use = !pt_skip(p, j.range_limit);
+    }
+    const unsigned m = __ballot_sync(FULL, use);
+    if (m == FULL) {
+#pragma unroll
+      for (int r = 0; r < 32; r++) {
+        sx += (double)__shfl_sync(FULL, p.x, r);
+        sy += (double)__shfl_sync(FULL, p.y, r);
+        sz += (double)__shfl_sync(FULL, p.z, r);
+      }
+      cnt += 32;
+    } else {
+      for (int r = 0; r < 32; r++) {
+        const float x = __shfl_sync(FULL, p.x, r), y = __shfl_sync(FULL, p.y, r), z = __shfl_sync(FULL, p.z, r);
+        if (m >> r & 1u) sx += (double)x, sy += (double)y, sz += (double)z, cnt++;
+      }
+    }
+  }
+  if (lane == 0) {
+    double *o = out + (size_t)blockIdx.x * 8;
+    o[3] = (double)cnt;
+    if (cnt > 0) o[0] = sx / (double)cnt, o[1] = sy / (double)cnt, o[2] = sz / (double)cnt;
+    unsigned long long *k = reinterpret_cast<unsigned long long *>(o);
+    k[4] = 0ull;   // maxDist = +0.0
+    k[5] = 0ull;   // ordered key of the smallest value
+    k[6] = ~0ull;  // ordered key of the largest value
+  }
+}
+__device__ __forceinline__ unsigned long long ord_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void k_extent(const BuildJob *__restrict__ jobs, const int *__restrict__ which, double *__restrict__ out) {
+  const BuildJob &j = jobs[which[blockIdx.y]];
+  double *o = out + (size_t)blockIdx.y * 8;
+  const double cx = o[0], cy = o[1], cz = o[2];
+  double md = 0.0;
+  unsigned long long kmax = 0ull, kmin = ~0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
+    const float4 p = j.pts[i];
+    if (pt_skip(p, j.range_limit)) continue;
+    const double d0 = cx - (double)p.x, d1 = cy - (double)p.y, d2 = cz - (double)p.z;
+    const double dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    md = dist > md ? dist : md;
+    const unsigned long long kk = ord_key(d2);
+    kmax = kk > kmax ? kk : kmax;
+    kmin = kk < kmin ? kk : kmin;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const double m2 = __shfl_xor_sync(FULL, md, off);
+    md = m2 > md ? m2 : md;
+    const unsigned long long a = __shfl_xor_sync(FULL, kmax, off), b = __shfl_xor_sync(FULL, kmin, off);
+    kmax = a > kmax ? a : kmax;
+    kmin = b < kmin ? b : kmin;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long *k = reinterpret_cast<unsigned long long *>(o);
+    atomicMax(k + 4, (unsigned long long)__double_as_longlong(md));  // md >= 0: bit pattern is monotone
+    atomicMax(k + 5, kmax);
+    atomicMin(k + 6, kmin);
+  }
+}
+
+// ---- binning -----------------------------------------------------------------------------------------
+__global__ void k_mark(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
+    const float4 p = j.pts[i];
+    int key = -1, ix, iy, iz;
+    if (!pt_skip(p, j.range_limit) && voxel_index(j.g, (double)p.x, (double)p.y, (double)p.z, ix, iy, iz) &&
+        in_grid(j.g, ix, iy, iz)) {
+      const int b = block_id(j.g, ix, iy, iz), bit = block_bit(ix, iy, iz);
+      key = b * 64 + bit;
+      atomicOr(j.amask + b, 1ull << bit);
+    }
+    j.pt_cell[i] = key;
+  }
+}
+
+// CTA-wide exclusive scan of one int per thread (blockDim.x == 1024); returns the exclusive prefix, total in *tot
+__device__ __forceinline__ int cta_excl_scan(int v, int *tot, int *wsum /*[32] shared*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_up_sync(FULL, inc, off);
+    if (lane >= off) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(FULL, w, off);
+      if (lane >= off) w += t;
+    }
+    wsum[lane] = w;  // inclusive
+  }
+  __syncthreads();
+  const int before = warp ? wsum[warp - 1] : 0;
+  *tot = wsum[31];
+  __syncthreads();
+  return before + inc - v;
+}
+
+// one CTA per map: abase = exclusive popcount scan of amask, compact list of touched blocks
+__global__ void __launch_bounds__(1024) k_blockscan(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.x];
+  __shared__ int wsum[32];
+  int run_c = 0, run_b = 0;
+  for (int base = 0; base < j.nblk; base += 1024) {
+    const int b = base + threadIdx.x;
+    const unsigned long long m = b < j.nblk ? j.amask[b] : 0ull;
+    const int c = __popcll(m), nz = m != 0ull;
+    int tc, tb;
+    const int ec = cta_excl_scan(c, &tc, wsum);
+    const int eb = cta_excl_scan(nz, &tb, wsum);
+    if (b < j.nblk) j.abase[b] = run_c + ec;
+    if (nz) j.tb_list[run_b + eb] = b;
+    run_c += tc, run_b += tb;
+  }
+  if (threadIdx.x == 0) j.counts[0] = run_c, j.counts[1] = run_b;
+}
+
+__global__ void k_count(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
+    const int key = j.pt_cell[i];
+    if (key < 0) continue;
+    const int b = key >> 6, bit = key & 63;
+    const int c = j.abase[b] + __popcll(j.amask[b] & ((1ull << bit) - 1ull));
+    j.pt_cell[i] = c;
+    atomicAdd(j.cnt + c, 1);
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_segscan(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.x];
+  __shared__ int wsum[32];
+  int run = 0;
+  for (int base = 0; base < j.n_all; base += 1024) {
+    const int c = base + threadIdx.x;
+    const int v = c < j.n_all ? j.cnt[c] : 0;
+    int t;
+    const int e = cta_excl_scan(v, &t, wsum);
+    if (c < j.n_all) j.seg_off[c] = run + e;
+    run += t;
+  }
+  if (threadIdx.x == 0) j.counts[4] = run;  // points binned
+}
+
+__global__ void k_scatter(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
+    const int c = j.pt_cell[i];
+    if (c < 0) continue;
+    j.seg_idx[j.seg_off[c] + atomicAdd(j.cursor + c, 1)] = i;
+  }
+}
+
+// ---- per-cell Gaussians --------------------------------------------------------------------------------
+// NDTCell::rescaleCovariance [upstream]: any eigenvalue <= 0 -> no Gaussian; clamp to >= max/1000 (fixture-pinned)
+__device__ bool rescale_covariance(double *cov) {
+  double ev[3], V[9];
+  eig_sym(3, cov, ev, V);
+  if (ev[0] <= 0 || ev[1] <= 0 || ev[2] <= 0) return false;
+  double maxe = ev[0] > ev[1] ? ev[0] : ev[1];
+  maxe = maxe > ev[2] ? maxe : ev[2];
+  bool recalc = false;
+  for (int i = 0; i < 3; i++)
+    if (maxe > ev[i] * 1000.0) ev[i] = maxe / 1000.0, recalc = true;
+  if (recalc)
+    for (int i = 0; i < 3; i++)
+      for (int k = 0; k < 3; k++) {
+        double s = 0;
+        for (int q = 0; q < 3; q++) s += V[i * 3 + q] * ev[q] * V[k * 3 + q];
+        cov[i * 3 + k] = s;
+      }
+  return true;
+}
+
+// one warp per touched block; its cells are processed one after another; every lane computes the same
+// sequential sums (points are fetched 32 at a time, coalesced by the gather, then broadcast by shuffles)
+__global__ void __launch_bounds__(256) k_cells(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int ntb = j.counts[1];
+  for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ntb; t += gridDim.x * 8) {
+    const int b = j.tb_list[t];
+    unsigned long long m = j.amask[b];
+    const unsigned long long om = j.o_amask ? j.o_amask[b] : 0ull;
+    int c = j.abase[b];
+    for (; m; m &= m - 1ull, c++) {
+      const int bit = __ffsll((long long)m) - 1;
+      // previous record
+      double mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      int N = 0, has = 0;
+      float occ = 0.f;
+      if (om >> bit & 1ull) {
+        const int oc = j.o_abase[b] + __popcll(om & ((1ull << bit) - 1ull));
+        for (int q = 0; q < 3; q++) mean[q] = j.o_cmean[(size_t)oc * 3 + q];
+        for (int q = 0; q < 9; q++) cov[q] = j.o_ccov[(size_t)oc * 9 + q];
+        N = j.o_cn[oc], has = j.o_chas[oc], occ = j.o_cocc[oc];
+      }
+      const int n = j.cnt[c];
+      if (n > 0) {
+        int *seg = j.seg_idx + j.seg_off[c];
+        int *srt = j.seg2 + j.seg_off[c];
+        // rank-sort the point ids (ascending = insertion order of NDTCell::points_)
+        if (n <= 32) {
+          const int v = lane < n ? seg[lane] : 0x7fffffff;
+          int r = 0;
+          for (int q = 0; q < n; q++) r += __shfl_sync(FULL, v, q) < v;
+          if (lane < n) srt[r] = v;
+        } else {
+          for (int e = lane; e < n; e += 32) {
+            const int v = seg[e];
+            int r = 0;
+            for (int q = 0; q < n; q++) r += seg[q] < v;
+            srt[r] = v;
+          }
+        }
+        __syncwarp();
+        // occupancy: += n*log(0.6/0.4), clamped (NDTCell::updateOccupancy)
+        {
+          float o2 = occ + (float)((double)n * j.log_occ);
+          o2 = o2 > j.occ_limit ? j.occ_limit : o2;
+          o2 = o2 < -j.occ_limit ? -j.occ_limit : o2;
+          occ = o2;
+        }
+        if (has || n >= 3) {
+          double ms[3] = {0, 0, 0};
+          for (int base = 0; base < n; base += 32) {
+            const int cntc = n - base < 32 ? n - base : 32;
+            float4 p = make_float4(0, 0, 0, 0);
+            if (lane < cntc) p = j.pts[srt[base + lane]];
+            for (int r = 0; r < cntc; r++) {
+              ms[0] += (double)__shfl_sync(FULL, p.x, r);
+              ms[1] += (double)__shfl_sync(FULL, p.y, r);
+              ms[2] += (double)__shfl_sync(FULL, p.z, r);
+            }
+          }
+          const double ml[3] = {ms[0] / (double)n, ms[1] / (double)n, ms[2] / (double)n};
+          double cs[6] = {0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz
+          for (int base = 0; base < n; base += 32) {
+            const int cntc = n - base < 32 ? n - base : 32;
+            float4 p = make_float4(0, 0, 0, 0);
+            if (lane < cntc) p = j.pts[srt[base + lane]];
+            for (int r = 0; r < cntc; r++) {
+              const double d0 = (double)__shfl_sync(FULL, p.x, r) - ml[0];
+              const double d1 = (double)__shfl_sync(FULL, p.y, r) - ml[1];
+              const double d2 = (double)__shfl_sync(FULL, p.z, r) - ml[2];
+              cs[0] += d0 * d0, cs[1] += d0 * d1, cs[2] += d0 * d2;
+              cs[3] += d1 * d1, cs[4] += d1 * d2, cs[5] += d2 * d2;
+            }
+          }
+          const double csum[9] = {cs[0], cs[1], cs[2], cs[1], cs[3], cs[4], cs[2], cs[4], cs[5]};
+          if (!has) {
+            for (int q = 0; q < 3; q++) mean[q] = ml[q];
+            for (int q = 0; q < 9; q++) cov[q] = csum[q] / (double)(n - 1);
+            N = n;
+          } else {  // pairwise (Chan) merge with the stored (N, mean, cov)
+            const double N0 = (double)N, n1 = (double)n;
+            double mS[3], cS[9], tv[3];
+            for (int q = 0; q < 3; q++) mS[q] = mean[q] * N0;
+            for (int q = 0; q < 9; q++) cS[q] = cov[q] * (N0 - 1.0);
+            const double w = N0 / (n1 * (N0 + n1));
+            for (int q = 0; q < 3; q++) tv[q] = (n1 / N0) * mS[q] - ms[q];
+            for (int a = 0; a < 3; a++)
+              for (int bb = 0; bb < 3; bb++) cS[a * 3 + bb] += csum[a * 3 + bb] + w * tv[a] * tv[bb];
+            for (int q = 0; q < 3; q++) mS[q] += ms[q];
+            double Nt = N0 + n1;
+            for (int q = 0; q < 3; q++) mean[q] = mS[q] / Nt;
+            for (int q = 0; q < 9; q++) cov[q] = cS[q] / (Nt - 1.0);
+            if (Nt > (double)j.maxnumpoints) Nt = (double)j.maxnumpoints;
+            N = (int)Nt;
+          }
+          has = rescale_covariance(cov) ? 1 : 0;
+        }
+      }
+      if (lane == 0) {
+        for (int q = 0; q < 3; q++) j.cmean[(size_t)c * 3 + q] = mean[q];
+        for (int q = 0; q < 9; q++) j.ccov[(size_t)c * 9 + q] = cov[q];
+        j.cn[c] = N, j.chas[c] = has, j.cocc[c] = occ;
+      }
+    }
+  }
+}
+
+// ---- Gaussian view ---------------------------------------------------------------------------------------
+// one CTA per map over the touched blocks: per-block Gaussian mask, exclusive scan -> base of the block in gcell
+__global__ void __launch_bounds__(1024) k_gscan(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.x];
+  __shared__ int wsum[32];
+  const int ntb = j.counts[1];
+  int run_c = 0, run_b = 0;
+  for (int base = 0; base < ntb; base += 1024) {
+    const int t = base + threadIdx.x;
+    unsigned long long gm = 0ull;
+    if (t < ntb) {
+      const int b = j.tb_list[t];
+      unsigned long long m = j.amask[b];
+      int c = j.abase[b];
+      for (; m; m &= m - 1ull, c++)
+        if (j.chas[c]) gm |= 1ull << (__ffsll((long long)m) - 1);
+    }
+    int tc, tb;
+    const int ec = cta_excl_scan(__popcll(gm), &tc, wsum);
+    cta_excl_scan(gm != 0ull, &tb, wsum);
+    if (t < ntb) j.gmask_t[t] = gm, j.gbase_t[t] = run_c + ec;
+    run_c += tc, run_b += tb;
+  }
+  if (threadIdx.x == 0) j.counts[2] = run_c, j.counts[3] = run_b;
+}
+
+// thread per touched block: publish the block in the hash table, copy its Gaussian cells to the compact view
+__global__ void k_gfill(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  const int ntb = j.counts[1];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntb; t += gridDim.x * blockDim.x) {
+    const unsigned long long gm = j.gmask_t[t];
+    if (!gm) continue;
+    const int b = j.tb_list[t];
+    unsigned h = hash_block(b, j.tsize);
+    for (;;) {
+      const int prev = atomicCAS(&j.table[h].key, -1, b);
+      if (prev == -1) break;
+      h = (h + 1) & (unsigned)(j.tsize - 1);
+    }
+    j.table[h].base = j.gbase_t[t];
+    j.table[h].mask = gm;
+    unsigned long long m = j.amask[b];
+    int c = j.abase[b], gs = j.gbase_t[t];
+    for (; m; m &= m - 1ull, c++) {
+      const int bit = __ffsll((long long)m) - 1;
+      if (!(gm >> bit & 1ull)) continue;
+      double *o = j.gcell + (size_t)gs * GC;
+      o[0] = j.cmean[(size_t)c * 3], o[1] = j.cmean[(size_t)c * 3 + 1], o[2] = j.cmean[(size_t)c * 3 + 2];
+      const double *cv = j.ccov + (size_t)c * 9;
+      o[3] = cv[0], o[4] = cv[1], o[5] = cv[2], o[6] = cv[4], o[7] = cv[5], o[8] = cv[8];
+      j.g2c[gs] = c;
+      gs++;
+    }
+  }
+}
+
+// ---- export / from_cells / parity hooks ------------------------------------------------------------------
+__global__ void k_export(const BuildJob *__restrict__ jobs, ndtb_cell *__restrict__ out) {
+  const BuildJob &j = jobs[0];
+  const int ntb = j.counts[1];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntb; t += gridDim.x * blockDim.x) {
+    const int b = j.tb_list[t];
+    const int bz = b % j.g.nb[2], by = (b / j.g.nb[2]) % j.g.nb[1], bx = b / (j.g.nb[2] * j.g.nb[1]);
+    unsigned long long m = j.amask[b];
+    int c = j.abase[b];
+    for (; m; m &= m - 1ull, c++) {
+      const int bit = __ffsll((long long)m) - 1;
+      ndtb_cell r;
+      for (int q = 0; q < 3; q++) r.mean[q] = j.cmean[(size_t)c * 3 + q];
+      const double *cv = j.ccov + (size_t)c * 9;
+      r.cov[0] = cv[0], r.cov[1] = cv[1], r.cov[2] = cv[2], r.cov[3] = cv[4], r.cov[4] = cv[5], r.cov[5] = cv[8];
+      r.n = j.cn[c], r.has_gaussian = j.chas[c];
+      r.idx[0] = bx * 4 + (bit >> 4), r.idx[1] = by * 4 + ((bit >> 2) & 3), r.idx[2] = bz * 4 + (bit & 3);
+      r.occ = j.cocc[c];
+      out[c] = r;
+    }
+  }
+}
+
+// from_cells: mark + place records given voxel indices (host resolved or from the mean)
+__global__ void k_cells_voxel(const BuildJob *__restrict__ jobs, const ndtb_cell *__restrict__ cells, int n, int use_idx,
+                              int *__restrict__ vox /*[n]: key or -1*/, int *__restrict__ err) {
+  const BuildJob &j = jobs[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int ix, iy, iz;
+    bool ok = true;
+    if (use_idx)
+      ix = cells[i].idx[0], iy = cells[i].idx[1], iz = cells[i].idx[2];
+    else
+      ok = voxel_index(j.g, (double)(float)cells[i].mean[0], (double)(float)cells[i].mean[1], (double)(float)cells[i].mean[2],
+                       ix, iy, iz);
+    if (!ok || !in_grid(j.g, ix, iy, iz)) {
+      vox[i] = -1;
+      atomicExch(err, 1);
+      continue;
+    }
+    const int b = block_id(j.g, ix, iy, iz), bit = block_bit(ix, iy, iz);
+    vox[i] = b * 64 + bit;
+    atomicOr(j.amask + b, 1ull << bit);
+  }
+}
+__global__ void k_cells_place(const BuildJob *__restrict__ jobs, const ndtb_cell *__restrict__ cells, int n,
+                              const int *__restrict__ vox) {
+  const BuildJob &j = jobs[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int key = vox[i];
+    if (key < 0) continue;
+    const int b = key >> 6, bit = key & 63;
+    const int c = j.abase[b] + __popcll(j.amask[b] & ((1ull << bit) - 1ull));
+    for (int q = 0; q < 3; q++) j.cmean[(size_t)c * 3 + q] = cells[i].mean[q];
+    const double *t = cells[i].cov;
+    const double full[9] = {t[0], t[1], t[2], t[1], t[3], t[4], t[2], t[4], t[5]};
+    for (int q = 0; q < 9; q++) j.ccov[(size_t)c * 9 + q] = full[q];
+    j.cn[c] = cells[i].n, j.chas[c] = cells[i].has_gaussian != 0, j.cocc[c] = cells[i].occ;
+  }
+}
+
+__global__ void k_point_indices(GridDesc g, const float4 *__restrict__ pts, int n, int *__restrict__ out,
+                                int *__restrict__ n_in) {
+  int local = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    int ix, iy, iz;
+    const bool ok = !(isnan(p.x) || isnan(p.y) || isnan(p.z)) && voxel_index(g, (double)p.x, (double)p.y, (double)p.z, ix, iy, iz);
+    if (!ok) ix = iy = iz = INT32_MIN;
+    out[3 * i] = ix, out[3 * i + 1] = iy, out[3 * i + 2] = iz;
+    if (ok && in_grid(g, ix, iy, iz)) local++;
+  }
+  local = __reduce_add_sync(FULL, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_in, local);
+}
+
+// ndt_feature::overlapNDTOccupancyScore (ndt_feature/include/ndt_feature/ndt_feature_node.h:213-252):
+// mean squared difference of rescaled occupancies over the initialised cells of `mov` mapped into `ref`.
+// Integer-free sums are accumulated per cell in (block, bit) order by ONE thread block with a fixed tree.
+__device__ __forceinline__ double occ_rescaled(float occ) { return 1.0 - 1.0 / (1.0 + exp((double)occ)); }
+__global__ void __launch_bounds__(256) k_overlap(const BuildJob *__restrict__ jobs /*[0]=ref,[1]=mov*/, const double *__restrict__ T16,
+                                                  double *__restrict__ out) {
+  const BuildJob &ref = jobs[0], &mov = jobs[1];
+  const Pose T = pose_from_cm(T16);
+  double sum = 0.0;
+  int nb = 0;
+  const int ntb = mov.counts[1];
+  for (int t = threadIdx.x; t < ntb; t += blockDim.x) {
+    const int b = mov.tb_list[t];
+    const int bz = b % mov.g.nb[2], by = (b / mov.g.nb[2]) % mov.g.nb[1], bx = b / (mov.g.nb[2] * mov.g.nb[1]);
+    unsigned long long m = mov.amask[b];
+    int c = mov.abase[b];
+    for (; m; m &= m - 1ull, c++) {
+      const int bit = __ffsll((long long)m) - 1;
+      const double mo = occ_rescaled(mov.cocc[c]);
+      if (mo == 0.5) continue;
+      const int idx[3] = {bx * 4 + (bit >> 4), by * 4 + ((bit >> 2) & 3), bz * 4 + (bit & 3)};
+      double e[3];
+      for (int a = 0; a < 3; a++) {
+        const int idc = (int)(mov.g.size[a] / 2.0);
+        e[a] = (double)(float)(mov.g.center[a] + (idx[a] - idc) * mov.g.cell[a]);  // NDTCell::getCenter is a float point
+      }
+      float pt[3];
+      for (int a = 0; a < 3; a++) pt[a] = (float)((T.R[a * 3] * e[0] + T.R[a * 3 + 1] * e[1] + T.R[a * 3 + 2] * e[2]) + T.t[a]);
+      int ix, iy, iz;
+      if (!voxel_index(ref.g, (double)pt[0], (double)pt[1], (double)pt[2], ix, iy, iz) || !in_grid(ref.g, ix, iy, iz)) continue;
+      const int rb = block_id(ref.g, ix, iy, iz), rbit = block_bit(ix, iy, iz);
+      const unsigned long long rm = ref.amask[rb];
+      if (!(rm >> rbit & 1ull)) continue;
+      const double ro = occ_rescaled(ref.cocc[ref.abase[rb] + __popcll(rm & ((1ull << rbit) - 1ull))]);
+      if (ro != 0.5) nb++, sum += (mo - ro) * (mo - ro);
+    }
+  }
+  __shared__ double ssum[8];
+  __shared__ int scnt[8];
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(FULL, sum, off), nb += __shfl_xor_sync(FULL, nb, off);
+  if ((threadIdx.x & 31) == 0) ssum[threadIdx.x >> 5] = sum, scnt[threadIdx.x >> 5] = nb;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    int n = 0;
+    for (int w = 0; w < 8; w++) s += ssum[w], n += scnt[w];
+    out[0] = n == 0 ? 1.0 : s / (1.0 * n);
+  }
+}
+
+// ---- launch wrappers (host) ---------------------------------------------------------------------------
+static inline int chunks_for(int n, int per) {
+  int c = (n + per - 1) / per;
+  return c < 1 ? 1 : (c > 1024 ? 1024 : c);
+}
+
+int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, double *d_out, cudaStream_t s) {
+  k_centroid<<<n_which, 32, 0, s>>>(d_jobs, d_which, d_out);
+  k_extent<<<dim3(chunks_for(max_pts, 1024), n_which), 256, 0, s>>>(d_jobs, d_which, d_out);
+  return 2;
+}
+int launch_mark(const BuildJob *d_jobs, int n, int max_pts, cudaStream_t s) {
+  k_mark<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
+  k_blockscan<<<n, 1024, 0, s>>>(d_jobs);
+  return 2;
+}
+int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, cudaStream_t s) {
+  k_count<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
+  k_segscan<<<n, 1024, 0, s>>>(d_jobs);
+  k_scatter<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
+  k_cells<<<dim3(chunks_for(max_ntb, 8), n), 256, 0, s>>>(d_jobs);
+  return 4;
+}
+int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s) {
+  k_gscan<<<n, 1024, 0, s>>>(d_jobs);
+  k_gfill<<<dim3(chunks_for(max_ntb, 128), n), 128, 0, s>>>(d_jobs);
+  return 2;
+}
+int launch_blockscan(const BuildJob *d_jobs, int n, cudaStream_t s) {
+  k_blockscan<<<n, 1024, 0, s>>>(d_jobs);
+  return 1;
+}
+int launch_export(const BuildJob *d_job, int ntb, ndtb_cell *d_out, cudaStream_t s) {
+  k_export<<<chunks_for(ntb, 128), 128, 0, s>>>(d_job, d_out);
+  return 1;
+}
+int launch_from_cells_voxel(const BuildJob *d_job, const ndtb_cell *d_cells, int n, int use_idx, int *d_vox, int *d_err,
+                            cudaStream_t s) {
+  k_cells_voxel<<<chunks_for(n, 256), 256, 0, s>>>(d_job, d_cells, n, use_idx, d_vox, d_err);
+  return 1;
+}
+int launch_from_cells_place(const BuildJob *d_job, const ndtb_cell *d_cells, int n, const int *d_vox, cudaStream_t s) {
+  k_cells_place<<<chunks_for(n, 256), 256, 0, s>>>(d_job, d_cells, n, d_vox);
+  return 1;
+}
+int launch_point_indices(const GridDesc &g, const float4 *d_pts, int n, int *d_out, int *d_nin, cudaStream_t s) {
+  k_point_indices<<<chunks_for(n, 1024), 256, 0, s>>>(g, d_pts, n, d_out, d_nin);
+  return 1;
+}
+int launch_overlap(const BuildJob *d_jobs2, const double *d_T16, double *d_out, cudaStream_t s) {
+  k_overlap<<<1, 256, 0, s>>>(d_jobs2, d_T16, d_out);
+  return 1;
+}
+
+}  // namespace ndtb

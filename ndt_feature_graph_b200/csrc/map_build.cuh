@@ -1,0 +1,62 @@
+// map_build.cuh — job descriptor and launchers of the map-build (K1) kernels; see map_build.cu.
+#pragma once
+
+#include "../../include/ndtb.h"
+#include "engine.cuh"
+
+namespace ndtb {
+
+// One map of a batched build.  Pointers address this map's slice of the batch slabs.
+struct BuildJob {
+  GridDesc g;
+  const float4 *pts;   // pending points (pcl::PointXYZ layout), device memory
+  int npts;
+  double range_limit;  // loadPointCloud range filter; <= 0: none
+  // all-cells structure (new layout)
+  unsigned long long *amask;  // [nblk] touched voxels per 4x4x4 block
+  int *abase;                 // [nblk] exclusive popcount scan
+  int nblk;
+  int *tb_list;  // compact list of touched blocks (ascending)
+  int *counts;   // [8]: 0 n_all, 1 n touched blocks, 2 n gaussian cells, 3 n gaussian blocks, 4 points binned
+  // per-point temporaries
+  int *pt_cell;  // [npts] voxel key (block*64+bit) then cell id; -1 = dropped
+  int *seg_idx;  // [npts] point ids grouped by cell (arbitrary order inside a cell)
+  int *seg2;     // [npts] the same, ascending inside each cell
+  // per-cell (valid after the popcount scan)
+  int n_all;
+  int *cnt, *seg_off, *cursor;
+  double *cmean;  // [n_all][3]
+  double *ccov;   // [n_all][9]
+  int *cn, *chas;
+  float *cocc;
+  // previous content of the map (merge path of computeNDTCells); null when fresh
+  const unsigned long long *o_amask;
+  const int *o_abase;
+  const double *o_cmean, *o_ccov;
+  const int *o_cn, *o_chas;
+  const float *o_cocc;
+  // Gaussian view
+  double *gcell;  // [ng][9]
+  int *g2c;       // [ng] -> all-cells index
+  HashEntry *table;
+  int tsize;
+  unsigned long long *gmask_t;  // per touched block
+  int *gbase_t;
+  unsigned maxnumpoints;
+  float occ_limit;
+  double log_occ;  // log(0.6/0.4) evaluated on the host
+};
+
+int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, double *d_out, cudaStream_t s);
+int launch_mark(const BuildJob *d_jobs, int n, int max_pts, cudaStream_t s);
+int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, cudaStream_t s);
+int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s);
+int launch_blockscan(const BuildJob *d_jobs, int n, cudaStream_t s);
+int launch_export(const BuildJob *d_job, int ntb, ndtb_cell *d_out, cudaStream_t s);
+int launch_from_cells_voxel(const BuildJob *d_job, const ndtb_cell *d_cells, int n, int use_idx, int *d_vox, int *d_err,
+                            cudaStream_t s);
+int launch_from_cells_place(const BuildJob *d_job, const ndtb_cell *d_cells, int n, const int *d_vox, cudaStream_t s);
+int launch_point_indices(const GridDesc &g, const float4 *d_pts, int n, int *d_out, int *d_nin, cudaStream_t s);
+int launch_overlap(const BuildJob *d_jobs2, const double *d_T16, double *d_out, cudaStream_t s);
+
+}  // namespace ndtb

@@ -1,0 +1,600 @@
+// optimizer.h — the Newton / More-Thuente controller of an NDT-D2D registration as a RESUMABLE state
+// machine: it never evaluates the score itself; it asks for "derivatives at pose P (with/without
+// Hessian)" and is resumed with the 28 reduced sums.  On the GPU one thread of the registration's
+// thread-block (cluster) runs it between derivative passes, so a whole registration is one launch.
+//
+// Control flow restated from the reference (no code copied; the loop structure, constants and quirks
+// are what defines the result):
+//   match / matchFusion      ndt_feature/include/ndt_feature/ndt_matcher_d2d_fusion.h:797-1155
+//                            (== upstream NDTMatcherD2D::match when no feature/soft terms are active;
+//                             call site ndt_feature/src/ndt_feature_src/ndt_feature_graph.cpp:273)
+//   lineSearchMT             ndt_matcher_d2d_fusion.h:390-793  (constants :400-408, info codes :655-678)
+//   lineSearchMTFusionTcov   ndt_matcher_d2d_fusion.h:37-385   (soft prior on the accumulated local pose)
+//   Mahalanobis prior        ndt_matcher_d2d_fusion.h:11-32
+//   MoreThuente::cstep       [upstream] == MINPACK dcstep, SURVEY.md Appendix A4
+//   increment convention     TR = Trans(p0..2)*Rx(p3)*Ry(p4)*Rz(p5), T <- TR*T  (:1035-1043)
+#pragma once
+
+#include "d2d_pair.h"
+
+#ifdef __CUDACC__
+#define NDTB_HDF __host__ __device__
+#else
+#define NDTB_HDF
+#endif
+
+namespace ndtb {
+
+struct Pose {
+  double R[9];  // row-major rotation
+  double t[3];
+};
+
+struct OptParams {
+  int itr_max, step_control, regularize;
+  int fusion, soft, tik;
+  double delta_score;
+  double Q[36];  // Tcov^-1 (fusion only), row-major
+};
+
+enum { PH_NEWTON = 0, PH_LS_INIT = 1, PH_LS_EVAL = 2, PH_FINAL = 3, PH_DONE = 4 };
+
+struct OptState {
+  int phase;
+  int want_hess;  // what the pending evaluation must compute
+  Pose Peval;     // pose of the pending evaluation
+  Pose T, Tbest, Tinit;
+  double score_best, score_here;
+  int itr, ret, exit_code, n_hess, n_grad, nonfinite;
+  double pose_local[6], x0[6], incr[6], scg[6];
+  // line search
+  int ls_soft;  // 1 while the (discarded) Tcov search of matchFusion :1008-1010 runs
+  double X[6];
+  double stp, dginit, dgtest, width, width1, finit, stx, fx, dgx, sty, fy, dgy, stmin, stmax;
+  int infoc, nfev, brackt, stage1;
+};
+
+// ------------------------------------------------------------------ small dense algebra
+NDTB_HDF inline void m3_mul(const double *A, const double *B, double *C) {
+  double t[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) t[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+  for (int i = 0; i < 9; i++) C[i] = t[i];
+}
+
+NDTB_HDF inline Pose pose_from_cm(const double *T) {
+  Pose P;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) P.R[i * 3 + j] = T[j * 4 + i];
+    P.t[i] = T[12 + i];
+  }
+  return P;
+}
+NDTB_HDF inline void pose_to_cm(const Pose &P, double *T) {
+  for (int i = 0; i < 16; i++) T[i] = 0.0;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) T[j * 4 + i] = P.R[i * 3 + j];
+    T[12 + i] = P.t[i];
+  }
+  T[15] = 1.0;
+}
+NDTB_HDF inline Pose pose_from_vec(const double *p) {
+  const double cx = cos(p[3]), sx = sin(p[3]), cy = cos(p[4]), sy = sin(p[4]), cz = cos(p[5]), sz = sin(p[5]);
+  const double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
+  const double Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
+  const double Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+  Pose P;
+  double t[9];
+  m3_mul(Rx, Ry, t);
+  m3_mul(t, Rz, P.R);
+  P.t[0] = p[0], P.t[1] = p[1], P.t[2] = p[2];
+  return P;
+}
+NDTB_HDF inline Pose pose_mul(const Pose &A, const Pose &B) {
+  Pose C;
+  m3_mul(A.R, B.R, C.R);
+  for (int i = 0; i < 3; i++)
+    C.t[i] = (A.R[i * 3] * B.t[0] + A.R[i * 3 + 1] * B.t[1] + A.R[i * 3 + 2] * B.t[2]) + A.t[i];
+  return C;
+}
+NDTB_HDF inline Pose pose_inverse(const Pose &A) {
+  Pose I;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) I.R[i * 3 + j] = A.R[j * 3 + i];
+  for (int i = 0; i < 3; i++) I.t[i] = -(I.R[i * 3] * A.t[0] + I.R[i * 3 + 1] * A.t[1] + I.R[i * 3 + 2] * A.t[2]);
+  return I;
+}
+// ndt_feature::getRobustYawFromAffine3d (ndt_feature/include/ndt_feature/utils.h:30-40)
+NDTB_HDF inline double robust_yaw(const Pose &P) {
+  double d = P.R[0];
+  d = d > 1.0 ? 1.0 : (d < -1.0 ? -1.0 : d);
+  const double a = acos(d);
+  return P.R[3] > 0 ? a : -a;
+}
+
+// cyclic Jacobi, symmetric n x n (n<=6), eigenvalues ascending, eigenvectors in the columns of V
+NDTB_HDF inline void eig_sym(int n, const double *Ain, double *evals, double *V) {
+  double A[36];
+  for (int i = 0; i < n * n; i++) A[i] = Ain[i];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const double a2 = A[i * n + j] * A[i * n + j];
+        if (i == j) diag += a2; else off += a2;
+      }
+    if (off <= 1e-32 * diag || off == 0.0) break;
+    for (int p = 0; p < n - 1; p++)
+      for (int q = p + 1; q < n; q++) {
+        const double apq = A[p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; k++) {
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - s * akq;
+          A[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - s * aqk;
+          A[q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          const double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - s * vkq;
+          V[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int order[6];
+  for (int i = 0; i < n; i++) order[i] = i;
+  for (int i = 1; i < n; i++) {  // stable insertion sort by eigenvalue
+    const int oi = order[i];
+    int j = i - 1;
+    while (j >= 0 && A[order[j] * n + order[j]] > A[oi * n + oi]) order[j + 1] = order[j], j--;
+    order[j + 1] = oi;
+  }
+  double Vt[36];
+  for (int j = 0; j < n; j++) {
+    evals[j] = A[order[j] * n + order[j]];
+    for (int i = 0; i < n; i++) Vt[i * n + j] = V[i * n + order[j]];
+  }
+  for (int i = 0; i < n * n; i++) V[i] = Vt[i];
+}
+
+// x = A^-1 b, LDL^T with symmetric diagonal pivoting (Eigen::LDLT semantics), n = 6
+NDTB_HDF inline void ldlt_solve6(const double *Ain, const double *b, double *x) {
+  const int n = 6;
+  double A[36];
+  for (int i = 0; i < 36; i++) A[i] = Ain[i];
+  int perm[6];
+  for (int i = 0; i < n; i++) perm[i] = i;
+  for (int k = 0; k < n; k++) {
+    int p = k;
+    double best = fabs(A[k * n + k]);
+    for (int i = k + 1; i < n; i++)
+      if (fabs(A[i * n + i]) > best) best = fabs(A[i * n + i]), p = i;
+    if (p != k) {
+      for (int j = 0; j < n; j++) { const double t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t; }
+      for (int i = 0; i < n; i++) { const double t = A[i * n + k]; A[i * n + k] = A[i * n + p]; A[i * n + p] = t; }
+      const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+    }
+    const double d = A[k * n + k];
+    if (d == 0.0) continue;
+    for (int i = k + 1; i < n; i++) A[i * n + k] /= d;
+    for (int i = k + 1; i < n; i++)
+      for (int j = k + 1; j <= i; j++) {
+        A[i * n + j] -= A[i * n + k] * d * A[j * n + k];
+        A[j * n + i] = A[i * n + j];
+      }
+  }
+  double y[6];
+  for (int i = 0; i < n; i++) y[i] = b[perm[i]];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < i; j++) y[i] -= A[i * n + j] * y[j];
+  for (int i = 0; i < n; i++) {
+    const double d = A[i * n + i];
+    y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0;
+  }
+  for (int i = n - 1; i >= 0; i--)
+    for (int j = i + 1; j < n; j++) y[i] -= A[j * n + i] * y[j];
+  for (int i = 0; i < n; i++) x[perm[i]] = y[i];
+}
+
+// general 6x6 inverse (Gauss-Jordan, partial pivoting); false if singular
+NDTB_HDF inline bool inv6(const double *Ain, double *Ainv) {
+  const int n = 6;
+  double M[6][12];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) M[i][j] = Ain[i * n + j], M[i][n + j] = (i == j) ? 1.0 : 0.0;
+  for (int c = 0; c < n; c++) {
+    int p = c;
+    for (int r = c + 1; r < n; r++)
+      if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
+    if (M[p][c] == 0.0 || M[p][c] != M[p][c]) return false;
+    if (p != c)
+      for (int j = 0; j < 2 * n; j++) { const double t = M[p][j]; M[p][j] = M[c][j]; M[c][j] = t; }
+    const double id = 1.0 / M[c][c];
+    for (int j = 0; j < 2 * n; j++) M[c][j] *= id;
+    for (int r = 0; r < n; r++)
+      if (r != c) {
+        const double f = M[r][c];
+        if (f != 0.0)
+          for (int j = 0; j < 2 * n; j++) M[r][j] -= f * M[c][j];
+      }
+  }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) Ainv[i * n + j] = M[i][n + j];
+  return true;
+}
+
+// ------------------------------------------------------------------ soft prior (ndt_matcher_d2d_fusion.h:11-32)
+NDTB_HDF inline double maha_score(const double *x, const double *C) {
+  double s = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) s += x[i] * C[i * 6 + j] * x[j];
+  return s;
+}
+NDTB_HDF inline void maha_gradient(const double *x, const double *C, double *g) {
+  for (int i = 0; i < 6; i++) {
+    g[i] = 0;
+    for (int j = 0; j < 6; j++) g[i] += (C[j * 6 + i] + C[i * 6 + j]) * x[j];
+  }
+}
+
+// ------------------------------------------------------------------ MoreThuente::cstep
+NDTB_HDF inline double mt_max3(double a, double b, double c) {
+  a = fabs(a), b = fabs(b), c = fabs(c);
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
+}
+NDTB_HDF inline int mt_cstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp,
+                             double fp, double dp, int &brackt, double stmin, double stmax) {
+  const double lo = stx < sty ? stx : sty, hi = stx > sty ? stx : sty;
+  if ((brackt && (stp <= lo || stp >= hi)) || (dx * (stp - stx) >= 0.0) || (stmax < stmin)) return 0;
+  const double sgnd = dp * (dx / fabs(dx));
+  int info, bound;
+  double theta, s, gamma, p, q, r, stpc, stpq, stpf;
+  if (fp > fx) {  // higher value: minimum bracketed
+    info = 1, bound = 1;
+    theta = 3 * (fx - fp) / (stp - stx) + dx + dp;
+    s = mt_max3(theta, dx, dp);
+    gamma = s * sqrt(((theta / s) * (theta / s)) - (dx / s) * (dp / s));
+    if (stp < stx) gamma = -gamma;
+    p = (gamma - dx) + theta;
+    q = ((gamma - dx) + gamma) + dp;
+    r = p / q;
+    stpc = stx + r * (stp - stx);
+    stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2) * (stp - stx);
+    stpf = (fabs(stpc - stx) < fabs(stpq - stx)) ? stpc : stpc + (stpq - stpc) / 2;
+    brackt = 1;
+  } else if (sgnd < 0.0) {  // lower value, derivatives of opposite sign
+    info = 2, bound = 0;
+    theta = 3 * (fx - fp) / (stp - stx) + dx + dp;
+    s = mt_max3(theta, dx, dp);
+    gamma = s * sqrt(((theta / s) * (theta / s)) - (dx / s) * (dp / s));
+    if (stp > stx) gamma = -gamma;
+    p = (gamma - dp) + theta;
+    q = ((gamma - dp) + gamma) + dx;
+    r = p / q;
+    stpc = stp + r * (stx - stp);
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
+    brackt = 1;
+  } else if (fabs(dp) < fabs(dx)) {  // lower value, same sign, derivative magnitude decreases
+    info = 3, bound = 1;
+    theta = 3 * (fx - fp) / (stp - stx) + dx + dp;
+    s = mt_max3(theta, dx, dp);
+    const double rad = (theta / s) * (theta / s) - (dx / s) * (dp / s);
+    gamma = s * sqrt(rad > 0.0 ? rad : 0.0);
+    if (stp > stx) gamma = -gamma;
+    p = (gamma - dp) + theta;
+    q = (gamma + (dx - dp)) + gamma;
+    r = p / q;
+    if (r < 0.0 && gamma != 0.0)
+      stpc = stp + r * (stx - stp);
+    else if (stp > stx)
+      stpc = stmax;
+    else
+      stpc = stmin;
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (brackt)
+      stpf = (fabs(stp - stpc) < fabs(stp - stpq)) ? stpc : stpq;
+    else
+      stpf = (fabs(stp - stpc) > fabs(stp - stpq)) ? stpc : stpq;
+  } else {  // lower value, same sign, derivative magnitude does not decrease
+    info = 4, bound = 0;
+    if (brackt) {
+      theta = 3 * (fp - fy) / (sty - stp) + dy + dp;
+      s = mt_max3(theta, dy, dp);
+      gamma = s * sqrt(((theta / s) * (theta / s)) - (dy / s) * (dp / s));
+      if (stp > sty) gamma = -gamma;
+      p = (gamma - dp) + theta;
+      q = ((gamma - dp) + gamma) + dy;
+      r = p / q;
+      stpf = stp + r * (sty - stp);
+    } else
+      stpf = stp > stx ? stmax : stmin;
+  }
+  if (fp > fx) {
+    sty = stp, fy = fp, dy = dp;
+  } else {
+    if (sgnd < 0.0) sty = stx, fy = fx, dy = dx;
+    stx = stp, fx = fp, dx = dp;
+  }
+  stpf = stmax < stpf ? stmax : stpf;
+  stpf = stmin > stpf ? stmin : stpf;
+  stp = stpf;
+  if (brackt && bound) {
+    const double lim = stx + 0.66 * (sty - stx);
+    if (sty > stx)
+      stp = lim < stp ? lim : stp;
+    else
+      stp = lim > stp ? lim : stp;
+  }
+  return info;
+}
+
+// ------------------------------------------------------------------ the state machine
+constexpr double LS_RECOVERY = 0.1, LS_FTOL = 0.11111, LS_GTOL = 0.99999, LS_STPMAX = 4.0, LS_STPMIN = 0.001,
+                 LS_XTOL = 0.01;
+constexpr int LS_MAXFEV = 40;
+
+NDTB_HDF inline void opt_request(OptState &s, const Pose &P, int hess, int phase) {
+  s.Peval = P;
+  s.want_hess = hess;
+  s.phase = phase;
+}
+
+NDTB_HDF inline void opt_begin(OptState &s, const OptParams &prm, const double *T0_colmajor) {
+  s.T = pose_from_cm(T0_colmajor);
+  s.Tbest = s.T;
+  s.Tinit = s.T;
+  s.score_best = prm.fusion ? 1.7976931348623157e308 : 2147483647.0;  // INT_MAX upstream
+  s.score_here = 0;
+  s.itr = 0, s.ret = 1, s.exit_code = 0, s.n_hess = 0, s.n_grad = 0, s.nonfinite = 0;
+  for (int i = 0; i < 6; i++) s.pose_local[i] = s.x0[i] = s.incr[i] = s.scg[i] = s.X[i] = 0.0;
+  s.ls_soft = 0;
+  opt_request(s, s.T, 1, PH_NEWTON);
+}
+
+NDTB_HDF inline void opt_finish(OptState &s) { s.phase = PH_DONE; }
+
+// head of the More-Thuente loop: bracket bookkeeping, clamp, then ask for the trial evaluation
+NDTB_HDF inline void ls_trial(OptState &s, const OptParams &prm) {
+  if (s.brackt) {
+    s.stmin = s.stx < s.sty ? s.stx : s.sty;
+    s.stmax = s.stx > s.sty ? s.stx : s.sty;
+  } else {
+    s.stmin = s.stx;
+    s.stmax = s.stp + 4 * (s.stp - s.stx);
+  }
+  s.stp = s.stp > LS_STPMIN ? s.stp : LS_STPMIN;
+  s.stp = s.stp < LS_STPMAX ? s.stp : LS_STPMAX;
+  if ((s.brackt && (s.stp <= s.stmin || s.stp >= s.stmax)) || (s.nfev >= LS_MAXFEV - 1) || (s.infoc == 0) ||
+      (s.brackt && (s.stmax - s.stmin <= LS_XTOL * s.stmax)))
+    s.stp = s.stx;
+  double pincr[6];
+  for (int i = 0; i < 6; i++) pincr[i] = s.stp * s.incr[i];
+  if (s.ls_soft)
+    for (int i = 0; i < 6; i++) s.X[i] += pincr[i];  // (sic) accumulates across evaluations, fusion.h:183
+  (void)prm;
+  opt_request(s, pose_mul(pose_from_vec(pincr), s.T), 0, PH_LS_EVAL);
+}
+
+NDTB_HDF inline void opt_apply_step(OptState &s, const OptParams &prm, double step) {
+  for (int i = 0; i < 6; i++) s.incr[i] *= step;
+  s.T = pose_mul(pose_from_vec(s.incr), s.T);
+  double nrm = 0;
+  for (int i = 0; i < 6; i++) s.pose_local[i] += s.incr[i], nrm += s.incr[i] * s.incr[i];
+  nrm = sqrt(nrm);
+  bool convergence = false;
+  if (s.itr > 0) convergence = nrm < prm.delta_score;
+  if (s.itr > prm.itr_max) convergence = true, s.ret = 0, s.exit_code = 3;
+  s.itr++;
+  if (!convergence)
+    opt_request(s, s.T, 1, PH_NEWTON);
+  else
+    opt_request(s, s.T, 0, PH_FINAL);
+}
+
+NDTB_HDF inline void ls_start(OptState &s, int soft) {
+  s.ls_soft = soft;
+  if (soft)
+    for (int i = 0; i < 6; i++) s.X[i] = s.pose_local[i];
+  opt_request(s, s.T, 0, PH_LS_INIT);
+}
+
+NDTB_HDF inline void ls_done(OptState &s, const OptParams &prm, double step) {
+  if (s.ls_soft) {  // fusion.h:1008-1023: the Tcov search result is overwritten by the NDT search
+    ls_start(s, 0);
+    return;
+  }
+  if (prm.fusion) step = step > 0.0 ? step : 0.0;
+  opt_apply_step(s, prm, step);
+}
+
+// Resume with the reduced sums of the evaluation that was requested: sums[0]=score, [1..6]=g,
+// [7..27]=H upper triangle (only when want_hess).
+NDTB_HDF inline void opt_advance(OptState &s, const OptParams &prm, const double *sums) {
+  if (!(sums[0] * 0.0 == 0.0)) s.nonfinite = 1;
+  switch (s.phase) {
+    case PH_NEWTON: {
+      s.n_hess++;
+      s.score_here = sums[0];
+      double g[6], H[36];
+      for (int i = 0; i < 6; i++) g[i] = sums[ACC_G + i];
+      for (int p = 0; p < 6; p++)
+        for (int q = p; q < 6; q++) H[p * 6 + q] = H[q * 6 + p] = sums[hidx(p, q)];
+      if (prm.soft) {
+        s.score_here += maha_score(s.pose_local, prm.Q);
+        double gm[6];
+        maha_gradient(s.pose_local, prm.Q, gm);
+        for (int i = 0; i < 6; i++) {
+          g[i] += gm[i];
+          for (int j = 0; j < 6; j++) H[i * 6 + j] += prm.Q[j * 6 + i] + prm.Q[i * 6 + j];
+        }
+      }
+      if (prm.tik) {  // fusion.h:894-911  g <- H^T g + Q x0 ; H <- H^T H + Q ; x0 = (x, y, 0, 0, 0, yaw) of T*Tinit^-1
+        const Pose X0 = pose_mul(s.T, pose_inverse(s.Tinit));
+        s.x0[0] = X0.t[0], s.x0[1] = X0.t[1], s.x0[2] = 0, s.x0[3] = 0, s.x0[4] = 0, s.x0[5] = robust_yaw(X0);
+        double Hn[36], gn[6];
+        for (int i = 0; i < 6; i++) {
+          gn[i] = 0;
+          for (int k = 0; k < 6; k++) gn[i] += H[k * 6 + i] * g[k] + prm.Q[i * 6 + k] * s.x0[k];
+          for (int j = 0; j < 6; j++) {
+            double a = 0;
+            for (int k = 0; k < 6; k++) a += H[k * 6 + i] * H[k * 6 + j];
+            Hn[i * 6 + j] = a + prm.Q[i * 6 + j];
+          }
+        }
+        for (int i = 0; i < 36; i++) H[i] = Hn[i];
+        for (int i = 0; i < 6; i++) g[i] = gn[i];
+        s.score_here += maha_score(s.x0, prm.Q);
+      }
+      for (int i = 0; i < 6; i++) s.scg[i] = g[i];
+      if (s.score_here < s.score_best) s.Tbest = s.T, s.score_best = s.score_here;
+      double evals[6], evecs[36];
+      eig_sym(6, H, evals, evecs);
+      const double minC = evals[0], maxC = evals[5];
+      double gnorm = 0;
+      for (int i = 0; i < 6; i++) gnorm += g[i] * g[i];
+      gnorm = sqrt(gnorm);
+      if (minC < 0) {
+        if (prm.regularize || prm.fusion) {
+          double reg = gnorm;
+          reg = reg + minC > 0 ? reg : 0.001 * maxC - minC;
+          for (int i = 0; i < 6; i++) evals[i] += reg;
+          for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) {
+              double a = 0;
+              for (int k = 0; k < 6; k++) a += evecs[i * 6 + k] * evals[k] * evecs[j * 6 + k];
+              H[i * 6 + j] = a;
+            }
+        } else {
+          if (s.score_here > s.score_best) s.T = s.Tbest;
+          s.exit_code = 4;
+          opt_finish(s);
+          return;
+        }
+      }
+      if (gnorm <= prm.delta_score) {
+        if (s.score_here > s.score_best) s.T = s.Tbest;
+        s.exit_code = 1;
+        opt_finish(s);
+        return;
+      }
+      double ng[6];
+      ldlt_solve6(H, g, ng);
+      double dginit = 0;
+      for (int i = 0; i < 6; i++) s.incr[i] = -ng[i], dginit += s.incr[i] * s.scg[i];
+      if (dginit > 0) {
+        if (s.score_here > s.score_best) s.T = s.Tbest;
+        s.exit_code = 2;
+        opt_finish(s);
+        return;
+      }
+      if (prm.step_control)
+        ls_start(s, prm.soft ? 1 : 0);
+      else
+        opt_apply_step(s, prm, 1.0);
+      return;
+    }
+    case PH_LS_INIT: {
+      s.n_grad++;
+      double score_init = sums[0], gh[6];
+      for (int i = 0; i < 6; i++) gh[i] = sums[ACC_G + i];
+      if (s.ls_soft) {
+        score_init += maha_score(s.X, prm.Q);
+        double gm[6];
+        maha_gradient(s.X, prm.Q, gm);
+        for (int i = 0; i < 6; i++) gh[i] += gm[i];
+      }
+      s.dginit = 0;
+      for (int i = 0; i < 6; i++) s.dginit += s.incr[i] * gh[i];
+      if (s.dginit >= 0.0) {
+        for (int i = 0; i < 6; i++) s.incr[i] = -s.incr[i];
+        s.dginit = -s.dginit;
+        if (s.dginit >= 0.0) {
+          ls_done(s, prm, LS_RECOVERY);
+          return;
+        }
+      }
+      s.stp = 1.0;
+      s.infoc = 1;
+      s.brackt = 0, s.stage1 = 1, s.nfev = 0;
+      s.dgtest = LS_FTOL * s.dginit;
+      s.width = LS_STPMAX - LS_STPMIN;
+      s.width1 = 2 * s.width;
+      s.finit = score_init;
+      s.stx = 0.0, s.fx = s.finit, s.dgx = s.dginit;
+      s.sty = 0.0, s.fy = s.finit, s.dgy = s.dginit;
+      ls_trial(s, prm);
+      return;
+    }
+    case PH_LS_EVAL: {
+      s.n_grad++;
+      double f = sums[0], gh[6];
+      for (int i = 0; i < 6; i++) gh[i] = sums[ACC_G + i];
+      if (s.ls_soft) {
+        f += maha_score(s.X, prm.Q);
+        double gm[6];
+        maha_gradient(s.X, prm.Q, gm);
+        for (int i = 0; i < 6; i++) gh[i] += gm[i];
+      }
+      double dg = 0;
+      for (int i = 0; i < 6; i++) dg += s.incr[i] * gh[i];
+      s.nfev++;
+      const double ftest1 = s.finit + s.stp * s.dgtest;
+      int info = 0;
+      if ((s.brackt && (s.stp <= s.stmin || s.stp >= s.stmax)) || (s.infoc == 0)) info = 6;
+      if ((s.stp == LS_STPMAX) && (f <= ftest1) && (dg <= s.dgtest)) info = 5;
+      if ((s.stp == LS_STPMIN) && ((f > ftest1) || (dg >= s.dgtest))) info = 4;
+      if (s.nfev >= LS_MAXFEV) info = 3;
+      if (s.brackt && (s.stmax - s.stmin <= LS_XTOL * s.stmax)) info = 2;
+      if ((f <= ftest1) && (fabs(dg) <= LS_GTOL * (-s.dginit))) info = 1;
+      if (info != 0) {
+        ls_done(s, prm, info != 1 ? LS_RECOVERY : s.stp);
+        return;
+      }
+      const double mtol = LS_FTOL < LS_GTOL ? LS_FTOL : LS_GTOL;
+      if (s.stage1 && (f <= ftest1) && (dg >= mtol * s.dginit)) s.stage1 = 0;
+      if (s.stage1 && (f <= s.fx) && (f > ftest1)) {
+        const double fm = f - s.stp * s.dgtest;
+        double fxm = s.fx - s.stx * s.dgtest, fym = s.fy - s.sty * s.dgtest;
+        const double dgm = dg - s.dgtest;
+        double dgxm = s.dgx - s.dgtest, dgym = s.dgy - s.dgtest;
+        s.infoc = mt_cstep(s.stx, fxm, dgxm, s.sty, fym, dgym, s.stp, fm, dgm, s.brackt, s.stmin, s.stmax);
+        s.fx = fxm + s.stx * s.dgtest;
+        s.fy = fym + s.sty * s.dgtest;
+        s.dgx = dgxm + s.dgtest;
+        s.dgy = dgym + s.dgtest;
+      } else {
+        s.infoc = mt_cstep(s.stx, s.fx, s.dgx, s.sty, s.fy, s.dgy, s.stp, f, dg, s.brackt, s.stmin, s.stmax);
+      }
+      if (s.brackt) {
+        if (fabs(s.sty - s.stx) >= 0.66 * s.width1) s.stp = s.stx + 0.5 * (s.sty - s.stx);
+        s.width1 = s.width;
+        s.width = fabs(s.sty - s.stx);
+      }
+      ls_trial(s, prm);
+      return;
+    }
+    case PH_FINAL: {
+      s.n_grad++;
+      s.score_here = sums[0];
+      if (prm.soft) s.score_here += maha_score(s.pose_local, prm.Q);
+      if (prm.tik) s.score_here += maha_score(s.x0, prm.Q);
+      if (s.score_here > s.score_best) s.T = s.Tbest;
+      opt_finish(s);
+      return;
+    }
+    default:
+      return;
+  }
+}
+
+}  // namespace ndtb

@@ -209,3 +209,40 @@ def perturb_pose(T, seed, dt=0.15, dr=0.03, planar=False):
     else:
         e = pose_from_xyzrpy(*rng.uniform(-dt, dt, 3), *rng.uniform(-dr, dr, 3))
     return e @ T
+
+
+# ------------------------------------------------------------------ batches of C2-shaped pairs (bench.py, tests)
+def odometry_guess(T, seed, dxy=0.15, dz=0.02, drp=0.005, dyaw=0.03):
+    """Vehicle-odometry-like initial guess: planar error dominates (x, y, yaw), small z / roll / pitch error."""
+    rng = np.random.default_rng(seed)
+    e = pose_from_xyzrpy(rng.uniform(-dxy, dxy), rng.uniform(-dxy, dxy), rng.uniform(-dz, dz), rng.uniform(-drp, drp),
+                         rng.uniform(-drp, drp), rng.uniform(-dyaw, dyaw))
+    return e @ T
+
+
+def _apply(G, cloud):
+    out = np.zeros_like(cloud)
+    out[:, :3] = (cloud[:, :3].astype(np.float64) @ G[:3, :3].T + G[:3, 3]).astype(np.float32)
+    return out
+
+
+def velodyne_batch(n_pairs, n_base=8, seed=0, n_rings=64, n_az=1563):
+    """n_pairs scan pairs of config C2.  n_base scenes are ray-cast (slow, numpy); every pair is a base pair moved by
+    its own rigid transform G (both scans), which changes the voxelisation of both maps, so all pairs are distinct
+    data.  Returns lists (target clouds, source clouds, initial guesses T0, true transforms D)."""
+    base = [velodyne_pair(100 * seed + b, n_rings, n_az) for b in range(min(n_base, n_pairs))]
+    rng = np.random.default_rng(9000 + seed)
+    tg, sr, T0s, Ds = [], [], [], []
+    for i in range(n_pairs):
+        ca, cb, D = base[i % len(base)]
+        if i < len(base):
+            G = np.eye(4)
+        else:
+            G = pose_from_xyzrpy(rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(-0.2, 0.2), 0.0, 0.0, rng.uniform(-np.pi, np.pi))
+        Gi = np.linalg.inv(G)
+        Di = G @ D @ Gi
+        tg.append(_apply(G, ca) if i >= len(base) else ca)
+        sr.append(_apply(G, cb) if i >= len(base) else cb)
+        Ds.append(Di)
+        T0s.append(odometry_guess(Di, 7000 + 31 * seed + i))
+    return tg, sr, T0s, Ds

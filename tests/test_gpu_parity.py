@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): voxel indices exact; cell N / flags exact and mean / covariance bit-exact
+(kernel (i) replays the oracle's operation order); score / gradient / Hessian to 1e-11 relative (different
+summation order); registered pose within 1e-4 in SE(3) log-norm (we hold 1e-8 on every case here).
+"""
+import numpy as np
+import pytest
+
+from ndt_feature_graph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-4  # north_star tolerance
+POSE_TIGHT = 1e-7  # what the deterministic fp64 path actually achieves
+
+
+def _build_pair(oracle, engine, ca, cb, mode="guess"):
+    import ndt_feature_graph_b200 as N
+
+    om, gm = [], []
+    for c in (ca, cb):
+        o = oracle.OracleMap(0.5)
+        g = N.NDTMap(engine, 0.5)
+        if mode == "fixed":
+            o.guess_size(0, 0, 0, 100, 100, 4)
+            g.guessSize(0, 0, 0, 100, 100, 4)
+        no = o.load_point_cloud(c, 60.0)
+        o.compute_cells()
+        ng = g.loadPointCloud(c, 60.0)
+        g.computeNDTCells()
+        assert no == ng
+        om.append(o)
+        gm.append(g)
+    return om, gm
+
+
+def _assert_cells_equal(oc, gc, exact=True):
+    assert oc.shape == gc.shape
+    assert np.array_equal(oc["idx"], gc["idx"])
+    assert np.array_equal(oc["n"], gc["n"])
+    assert np.array_equal(oc["has_gaussian"], gc["has_gaussian"])
+    assert np.array_equal(oc["occ"], gc["occ"])
+    if exact:
+        assert np.array_equal(oc["mean"], gc["mean"])
+        assert np.array_equal(oc["cov"], gc["cov"])
+    else:
+        np.testing.assert_allclose(gc["mean"], oc["mean"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(gc["cov"], oc["cov"], rtol=1e-9, atol=1e-15)
+
+
+@pytest.fixture(scope="module")
+def c1(oracle, engine):
+    ca, cb, D = synth.laser2d_pair(0)
+    om, gm = _build_pair(oracle, engine, ca, cb, "fixed")
+    return ca, cb, D, om, gm
+
+
+@pytest.fixture(scope="module")
+def c2small(oracle, engine):
+    ca, cb, D = synth.velodyne_pair(1, n_rings=32, n_az=600)
+    om, gm = _build_pair(oracle, engine, ca, cb, "guess")
+    return ca, cb, D, om, gm
+
+
+# ------------------------------------------------------------------ kernel (i): map build
+def test_voxel_indices_exact(oracle, engine, c1, c2small):
+    for ca, cb, D, om, gm in (c1, c2small):
+        for c, o, g in zip((ca, cb), om, gm):
+            gi, nin = g.point_indices(c)
+            assert np.array_equal(gi, o.point_indices(c))
+            go, gg = o.grid(), g.grid()
+            for a, b in zip(go, gg):
+                assert np.array_equal(a, b)
+
+
+def test_cells_bit_exact(oracle, engine, c1, c2small):
+    for ca, cb, D, om, gm in (c1, c2small):
+        for o, g in zip(om, gm):
+            _assert_cells_equal(o.export_cells(False), g.export_cells(False))
+            assert g.numberOfActiveCells() == o.num_cells(True)
+
+
+def test_edge_inputs(oracle, engine):
+    import ndt_feature_graph_b200 as N
+
+    # empty cloud, NaNs, out-of-range, out-of-grid points, duplicates, < 3 points per cell
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-3, 3, (500, 4)).astype(np.float32)
+    pts[::7, 0] = np.nan
+    pts[5::11] *= 40.0  # far outside the 10 m grid
+    pts[3::13] = pts[3]  # duplicates -> zero variance cell candidates
+    for cloud in (pts, pts[:2], np.zeros((0, 4), np.float32)):
+        o = oracle.OracleMap(0.5)
+        g = N.NDTMap(engine, 0.5)
+        o.guess_size(0.1, -0.2, 0.3, 10, 10, 10)
+        g.guessSize(0.1, -0.2, 0.3, 10, 10, 10)
+        assert o.load_point_cloud(cloud, 30.0) == g.loadPointCloud(cloud, 30.0)
+        o.compute_cells()
+        g.computeNDTCells()
+        _assert_cells_equal(o.export_cells(False), g.export_cells(False))
+    # guess-size path with nothing usable: no grid, no cells
+    g = N.NDTMap(engine, 0.5)
+    assert g.loadPointCloud(np.full((4, 4), np.nan, np.float32)) == 0
+    assert g.num_cells(False) == 0
+
+
+def test_incremental_merge(oracle, engine):
+    """initialize + addPointCloud/computeNDTCells twice (ndt_feature_fuser_hmt.cpp:87-94 then :485-486)."""
+    import ndt_feature_graph_b200 as N
+
+    ca, cb, D = synth.laser2d_pair(2, n_rays=3000)
+    o = oracle.OracleMap(0.5)
+    g = N.NDTMap(engine, 0.5)
+    o.initialize(0, 0, 0, 100, 100, 1)
+    g.initialize(0, 0, 0, 100, 100, 1)
+    for cloud, maxpts in ((ca, int(1e5)), (ca[::2] + np.float32(0.01), 40), (cb, 40)):
+        assert o.add_points(cloud) == g.addPointCloud(cloud)
+        o.compute_cells(maxpts, 255.0)
+        g.computeNDTCells(maxpts, 255.0)
+        _assert_cells_equal(o.export_cells(False), g.export_cells(False))
+
+
+# ------------------------------------------------------------------ kernel (ii): derivatives
+def _rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+def test_derivatives_fixture_maps(oracle, engine, golden, oracle_fixture_maps, gpu_fixture_maps):
+    import ndt_feature_graph_b200 as N
+
+    m = N.NDTMatcherD2D(engine)
+    for k in range(7):
+        T = golden[f"Todom{k}"]
+        for nb in (0, 1, 2, 3):
+            p = oracle.default_params(n_neighbours=nb)
+            m.n_neighbours = nb
+            so, go, Ho, no = oracle.d2d_derivatives(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T, p, True)
+            sg, gg, Hg, ng = m.derivativesNDT(gpu_fixture_maps[k], gpu_fixture_maps[k + 1], T, True)
+            assert no == ng
+            assert abs(sg - so) <= 1e-11 * max(1.0, abs(so))
+            assert _rel(gg, go) < 1e-10
+            assert _rel(Hg, Ho) < 1e-10
+            sg2, gg2, _, ng2 = m.derivativesNDT(gpu_fixture_maps[k], gpu_fixture_maps[k + 1], T, False)
+            assert ng2 == ng and abs(sg2 - so) <= 1e-11 * max(1.0, abs(so)) and _rel(gg2, go) < 1e-10
+
+
+def test_derivatives_synthetic(oracle, engine, c1, c2small):
+    import ndt_feature_graph_b200 as N
+
+    m = N.NDTMatcherD2D(engine)
+    for ca, cb, D, om, gm in (c1, c2small):
+        for seed in range(3):
+            T = synth.perturb_pose(D, seed, planar=False)
+            so, go, Ho, no = oracle.d2d_derivatives(om[0], om[1], T)
+            sg, gg, Hg, ng = m.derivativesNDT(gm[0], gm[1], T, True)
+            assert no == ng and no > 0
+            assert abs(sg - so) <= 1e-11 * abs(so)
+            assert _rel(gg, go) < 1e-10 and _rel(Hg, Ho) < 1e-10
+
+
+# ------------------------------------------------------------------ match / covariance
+def _check_result(ro, rg):
+    err = synth.pose_error(ro.pose(), rg.pose())
+    assert err < POSE_TIGHT, err
+    assert (ro.converged, ro.iterations, ro.n_hess_passes, ro.n_grad_passes, ro.exit_code) == (
+        rg.converged, rg.iterations, rg.n_hess_passes, rg.n_grad_passes, rg.exit_code)
+    assert ro.pose_changed == rg.pose_changed
+    assert abs(ro.score - rg.score) <= 1e-9 * max(1.0, abs(ro.score))
+
+
+@pytest.mark.parametrize("delta_score", [1e-3, 1e-6])
+def test_match_fixture_pairs(oracle, engine, golden, oracle_fixture_maps, gpu_fixture_maps, delta_score):
+    import ndt_feature_graph_b200 as N
+
+    m = N.NDTMatcherD2D(engine, delta_score=delta_score)
+    p = oracle.default_params(delta_score=delta_score)
+    for k in range(7):
+        T0 = golden[f"Todom{k}"]
+        ro = oracle.d2d_match(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T0, p)
+        rg = m.match(gpu_fixture_maps[k], gpu_fixture_maps[k + 1], T0)
+        _check_result(ro, rg)
+        # sanity envelope of SURVEY.md §4: within 0.12 m / 0.012 rad of the fuser's own estimate
+        F = golden[f"Tfuse{k}"]
+        Tg = rg.pose()
+        assert np.hypot(Tg[0, 3] - F[0, 3], Tg[1, 3] - F[1, 3]) < 0.12
+        assert abs(synth.robust_yaw(Tg) - synth.robust_yaw(F)) < 0.012
+
+
+def _oracle_is_stable(oracle, ot, os_, T0, ro, **kw):
+    """The optimiser is discontinuous (More-Thuente branches, neighbourhoods that change with the pose): from a poor
+    start a registration can hop between basins and then ANY change of summation order is amplified to O(1) pose
+    differences (SURVEY.md §7 hard part b).  Such a case cannot pin parity; it is detected with the oracle alone:
+    re-run it with OpenMP partial sums (3 threads = another summation order) and require it to agree with itself."""
+    r3 = oracle.d2d_match(ot, os_, T0, oracle.default_params(n_threads=3, **kw))
+    return synth.pose_error(ro.pose(), r3.pose()) < 1e-9 and ro.n_grad_passes == r3.n_grad_passes
+
+
+def test_match_synthetic(oracle, engine, c1, c2small):
+    import ndt_feature_graph_b200 as N
+
+    m = N.NDTMatcherD2D(engine)
+    n_stable = n_total = 0
+    for (ca, cb, D, om, gm), planar in ((c1, True), (c2small, False)):
+        for seed in range(8):
+            # odometry-like starts plus two rough 6-DoF ones (those may be chaotic -> gated)
+            T0 = synth.perturb_pose(D, 10 + seed, planar=planar) if (seed < 2 or planar) else synth.odometry_guess(D, 10 + seed)
+            ro = oracle.d2d_match(om[0], om[1], T0)
+            rg = m.match(gm[0], gm[1], T0)
+            n_total += 1
+            if not _oracle_is_stable(oracle, om[0], om[1], T0, ro):
+                continue  # chaotic start: the oracle does not even reproduce itself
+            n_stable += 1
+            _check_result(ro, rg)
+            if seed >= 2:
+                assert synth.pose_error(rg.pose(), D) < 0.05  # from an odometry-like start it actually registers
+    assert n_stable >= n_total - 3, (n_stable, n_total)
+
+
+def test_match_identity_guess_and_no_overlap(oracle, engine, c1):
+    import ndt_feature_graph_b200 as N
+
+    ca, cb, D, om, gm = c1
+    m = N.NDTMatcherD2D(engine)
+    _check_result(oracle.d2d_match(om[0], om[1], np.eye(4)), m.match(gm[0], gm[1], np.eye(4), useInitialGuess=False))
+    far = synth.pose2d(500.0, 500.0, 0.3)  # no neighbours at all: gradient vanishes, pose unchanged
+    ro, rg = oracle.d2d_match(om[0], om[1], far), m.match(gm[0], gm[1], far)
+    _check_result(ro, rg)
+    assert rg.pose_changed == 0 and rg.exit_code == 1
+
+
+def test_fusion_match(oracle, engine, golden, oracle_fixture_maps, gpu_fixture_maps):
+    import ndt_feature_graph_b200 as N
+
+    Tcov = np.diag([0.01, 0.01, 1e-4, 1e-6, 1e-6, 0.001])
+    for soft, tik in ((1, 0), (0, 1), (1, 1)):
+        m = N.NDTMatcherD2D(engine, delta_score=1e-6, use_soft_constraints=soft, use_tikhonov=tik)
+        p = oracle.default_params(delta_score=1e-6, use_soft_constraints=soft, use_tikhonov=tik)
+        for k in (1, 4, 6):
+            T0 = golden[f"Todom{k}"]
+            ro = oracle.fusion_match(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T0, Tcov, p)
+            rg = m.matchFusion(gpu_fixture_maps[k], gpu_fixture_maps[k + 1], T0, Tcov)
+            _check_result(ro, rg)
+
+
+def test_covariance(oracle, engine, golden, oracle_fixture_maps, gpu_fixture_maps, c2small):
+    import ndt_feature_graph_b200 as N
+
+    m = N.NDTMatcherD2D(engine)
+    cases = [(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], gpu_fixture_maps[k], gpu_fixture_maps[k + 1],
+              golden[f"Tfuse{k}"]) for k in range(7)]
+    ca, cb, D, om, gm = c2small
+    cases.append((om[0], om[1], gm[0], gm[1], D))
+    for ot, os_, gt, gs, T in cases:
+        rc, co = oracle.d2d_covariance(ot, os_, T)
+        ok, cg = m.covariance(gt, gs, T)
+        assert rc == 0 and ok
+        np.testing.assert_allclose(cg, co, rtol=1e-7, atol=1e-9 * np.abs(co).max())
+        assert np.allclose(cg, cg.T, rtol=1e-9, atol=1e-18)
+
+
+def test_match_batch_with_covariance(oracle, engine, golden, oracle_fixture_maps, gpu_fixture_maps):
+    """updateLinksUsingNDTRegistration over the 7 shipped consecutive node pairs (+ an unchanged-pose edge)."""
+    T0s = [golden[f"Todom{k}"] for k in range(7)] + [synth.pose2d(900.0, 0.0, 0.0)]
+    ot = oracle_fixture_maps[:7] + [oracle_fixture_maps[0]]
+    os_ = oracle_fixture_maps[1:8] + [oracle_fixture_maps[1]]
+    gt = gpu_fixture_maps[:7] + [gpu_fixture_maps[0]]
+    gs = gpu_fixture_maps[1:8] + [gpu_fixture_maps[1]]
+    ro, co = oracle.d2d_match_batch(ot, os_, T0s, with_covariance=True)
+    rg, cg = engine.match_batch(gt, gs, T0s, with_covariance=True)
+    for e in range(8):
+        Tg = rg["T"][e].reshape(4, 4).T
+        assert synth.pose_error(ro[e].pose(), Tg) < POSE_TIGHT
+        assert ro[e].pose_changed == rg["pose_changed"][e]
+        np.testing.assert_allclose(cg[e], co[e], rtol=1e-6, atol=1e-9 * np.abs(co[e]).max())
+    assert np.array_equal(cg[7], 0.02 * np.eye(6))  # ndt_feature_graph.cpp:300-310
+
+
+def test_register_scans_matches_stepwise(oracle, engine, c2small):
+    """The batched front-end entry point equals map build + match + covariance done step by step on the oracle."""
+    ca, cb, D, om, gm = c2small
+    T0 = synth.perturb_pose(D, 77)
+    # register_scans uses no range limit: rebuild oracle maps accordingly
+    oms = []
+    for c in (ca, cb):
+        o = oracle.OracleMap(0.5)
+        o.load_point_cloud(c, -1.0)
+        o.compute_cells()
+        oms.append(o)
+    ro = oracle.d2d_match(oms[0], oms[1], T0)
+    rc, co = oracle.d2d_covariance(oms[0], oms[1], ro.pose())
+    res, cov = engine.register_scans([ca, ca], [cb, cb], [T0, T0], cell=0.5, with_covariance=True)
+    for e in range(2):
+        assert synth.pose_error(ro.pose(), res["T"][e].reshape(4, 4).T) < POSE_TIGHT
+        assert res["iterations"][e] == ro.iterations
+        np.testing.assert_allclose(cov[e], co, rtol=1e-6, atol=1e-9 * np.abs(co).max())
+    assert np.array_equal(res["T"][0], res["T"][1])  # deterministic
+
+
+def test_overlap_score(oracle, engine, c1):
+    ca, cb, D, om, gm = c1
+    for T in (D, np.eye(4), synth.pose2d(3.0, -2.0, 0.7)):
+        so = oracle.overlap_occupancy_score(om[0], om[1], T)
+        sg = gm[0].overlapNDTOccupancyScore(gm[1], T)
+        assert abs(so - sg) <= 1e-12 * max(1.0, abs(so))
+
+
+def test_determinism(engine, c2small):
+    import ndt_feature_graph_b200 as N
+
+    ca, cb, D, om, gm = c2small
+    m = N.NDTMatcherD2D(engine)
+    T0 = synth.perturb_pose(D, 5)
+    a = m.match(gm[0], gm[1], T0)
+    b = m.match(gm[0], gm[1], T0)
+    assert list(a.T) == list(b.T) and a.score == b.score

@@ -81,9 +81,10 @@ typedef struct ndtb_params { /* NDTMatcherD2D public knobs + matchFusion flags *
   double lfd1, lfd2;       /* 1, 0.05 */
   int32_t use_soft_constraints; /* matchFusion only */
   int32_t use_tikhonov;         /* matchFusion only */
-  int32_t ctas_per_match;  /* engine knob: CTAs (one thread-block cluster) cooperating on one registration;
-                              0 = auto (1 for batches >= #SMs, up to 8 for small batches) */
-  int32_t pad_;
+  int32_t ctas_per_match;  /* engine knob: CTAs (one thread-block cluster, 1/2/4/8) cooperating on one
+                              registration; 0 = auto (1 for batches >= #SMs, up to 8 for small batches) */
+  int32_t pass_budget;     /* engine knob: derivative passes a registration may use in the first (1-CTA) launch before
+                              it is handed to a second launch on 8-CTA clusters (stragglers); 0 = auto, <0 = never */
 } ndtb_params;
 
 /* ndtb_result.status bits (SURVEY.md §5 "failure detection") */
@@ -102,13 +103,16 @@ typedef struct ndtb_result {
   int32_t converged;       /* return value of match() */
   int32_t iterations;
   int32_t n_hess_passes;   /* derivativesNDT calls with Hessian */
-  int32_t n_grad_passes;   /* gradient-only derivativesNDT calls */
+  int32_t n_grad_passes;   /* gradient-only derivativesNDT calls the reference makes */
   int32_t pose_changed;
   int32_t exit_code;       /* 0 loop end, 1 gradient vanished, 2 dginit>0, 3 itr_max, 4 no regularisation */
   int32_t status;          /* NDTB_ST_* */
   int32_t n_src_cells;     /* Gaussian cells of the source map (Cs) */
   int32_t n_tgt_cells;     /* Gaussian cells of the target map (Ct) */
   int32_t tgt_table_entries; /* 16-byte entries of the target's block table (probe window W) */
+  float kernel_ms;         /* SM-milliseconds the registration kernel spent on this edge (CTAs x device time) */
+  int32_t n_exec_passes;   /* derivative passes actually run on the device (the reference repeats some evaluations
+                              at an already evaluated pose; those are answered from the previous pass) */
 } ndtb_result;
 
 /* ---- context ---------------------------------------------------------------------------------- */

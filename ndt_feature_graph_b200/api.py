@@ -20,7 +20,8 @@ HOST, DEVICE = 0, 1
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libndtb.so")
+    # NDTB_LIB: alternative build of the same library (kernel-variant A/B runs); default = the in-tree build
+    return os.environ.get("NDTB_LIB") or os.path.join(_HERE, "lib", "libndtb.so")
 
 
 class NdtbError(RuntimeError):
@@ -50,7 +51,7 @@ class Params(C.Structure):
         ("use_soft_constraints", C.c_int32),
         ("use_tikhonov", C.c_int32),
         ("ctas_per_match", C.c_int32),
-        ("pad_", C.c_int32),
+        ("pass_budget", C.c_int32),
     ]
 
 
@@ -69,6 +70,8 @@ class Result(C.Structure):
         ("n_src_cells", C.c_int32),
         ("n_tgt_cells", C.c_int32),
         ("tgt_table_entries", C.c_int32),
+        ("kernel_ms", C.c_float),
+        ("n_exec_passes", C.c_int32),
     ]
 
     def pose(self):
@@ -78,9 +81,9 @@ class Result(C.Structure):
 RESULT_DTYPE = np.dtype(
     [("T", "<f8", 16), ("score", "<f8"), ("score_best", "<f8"), ("converged", "<i4"), ("iterations", "<i4"),
      ("n_hess_passes", "<i4"), ("n_grad_passes", "<i4"), ("pose_changed", "<i4"), ("exit_code", "<i4"),
-     ("status", "<i4"), ("n_src_cells", "<i4"), ("n_tgt_cells", "<i4"), ("tgt_table_entries", "<i4")]
+     ("status", "<i4"), ("n_src_cells", "<i4"), ("n_tgt_cells", "<i4"), ("tgt_table_entries", "<i4"), ("kernel_ms", "<f4"), ("n_exec_passes", "<i4")]
 )
-assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 184
+assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 192
 
 _lib = None
 

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -18,7 +20,10 @@
 namespace ndtb {
 // d2d.cu
 size_t match_smem_bytes(int table_entries);
-cudaError_t launch_match(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, ndtb_result *d_out, cudaStream_t stream);
+size_t opt_state_bytes();
+cudaError_t launch_match(const MatchJob *d_jobs, const int *d_job_ids, int n_slots, int cluster, const MatchConfig &cfg,
+                         ndtb_result *d_out, void *d_states, int resume, int pass_budget, int *d_unfinished,
+                         cudaStream_t stream);
 cudaError_t launch_derivatives(const MatchJob *d_job, const MatchConfig &cfg, bool hess, int n_ctas, double *d_partial,
                                double *d_out29, cudaStream_t stream);
 cudaError_t launch_covariance(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, const ndtb_result *d_res,
@@ -53,6 +58,16 @@ struct ndtb_ctx {
 
 namespace {
 
+// NDTB_PROFILE=1: host-side phase timer (synchronises the stream at every mark; debugging aid, never on in benchmarks)
+struct PhaseTimer {
+  ndtb_ctx *ctx;
+  bool on;
+  const char *what;
+  std::chrono::steady_clock::time_point t0;
+  PhaseTimer(ndtb_ctx *c, const char *w);
+  void mark(const char *label);
+};
+
 struct Slab {  // one stream-ordered device allocation shared by the maps of a batch
   ndtb_ctx *ctx;
   char *p = nullptr;
@@ -69,6 +84,22 @@ int slab_alloc(ndtb_ctx *ctx, size_t bytes, SlabP &out) {
   out->bytes = bytes ? bytes : 256;
   CU_TRY(ctx, cudaMallocAsync((void **)&out->p, out->bytes, ctx->stream));
   return NDTB_OK;
+}
+
+PhaseTimer::PhaseTimer(ndtb_ctx *c, const char *w) : ctx(c), what(w) {
+  static const bool env = std::getenv("NDTB_PROFILE") != nullptr;
+  on = env;
+  if (on) {
+    cudaStreamSynchronize(ctx->stream);
+    t0 = std::chrono::steady_clock::now();
+  }
+}
+void PhaseTimer::mark(const char *label) {
+  if (!on) return;
+  cudaStreamSynchronize(ctx->stream);
+  const auto t1 = std::chrono::steady_clock::now();
+  std::fprintf(stderr, "[ndtb] %s/%s: %.3f ms\n", what, label, std::chrono::duration<double, std::milli>(t1 - t0).count());
+  t0 = t1;
 }
 
 struct Carver {
@@ -231,6 +262,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
   const int M = (int)maps.size();
   if (M == 0) return NDTB_OK;
   cudaStream_t st = ctx->stream;
+  PhaseTimer pt(ctx, "build");
   std::vector<BuildJob> jobs(M);
   std::memset(jobs.data(), 0, sizeof(BuildJob) * M);
   int max_pts = 1;
@@ -278,6 +310,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     m->nblk = (int)m->nblocks();
   }
 
+  pt.mark("grids");
   // ---- phase B: mark touched voxels, number the cells
   std::vector<SlabP> keep_old;  // previous storage of merged maps stays alive until the end of the build
   Carver cb, ct;
@@ -285,6 +318,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     size_t amask, abase, tbl, counts, ptc, seg, seg2;
   };
   std::vector<OffB> ob(M);
+  const size_t o_counts_all = cb.take(32 * (size_t)M);  // contiguous: one D2H copy for the whole batch
   for (int i = 0; i < M; i++) {
     if (empty[i]) continue;
     ndtb_map *m = maps[i];
@@ -292,7 +326,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     ob[i].amask = cb.take(8 * (size_t)m->nblk);
     ob[i].abase = cb.take(4 * (size_t)m->nblk);
     ob[i].tbl = cb.take(4 * (size_t)std::max<int64_t>(tb_cap, 1));
-    ob[i].counts = cb.take(32);
+    ob[i].counts = o_counts_all + 32 * (size_t)i;
     ob[i].ptc = ct.take(4 * (size_t)pts[i].n);
     ob[i].seg = ct.take(4 * (size_t)pts[i].n);
     ob[i].seg2 = ct.take(4 * (size_t)pts[i].n);
@@ -329,36 +363,42 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
   if (L == 0) return NDTB_OK;
   CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
   ctx->launches += launch_mark(d_jobs, L, max_pts, st);
-  std::vector<int> cnts(8 * (size_t)L);
-  for (int l = 0; l < L; l++)
-    CU_TRY(ctx, cudaMemcpyAsync(&cnts[8 * l], live[l].counts, 32, cudaMemcpyDeviceToHost, st));
+  std::vector<int> cnts_all(8 * (size_t)M), cnts(8 * (size_t)L);
+  CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
+  for (int l = 0; l < L; l++) std::memcpy(&cnts[8 * l], &cnts_all[8 * (size_t)live_idx[l]], 32);
+  pt.mark("mark+scan");
 
   // ---- phase C: cell records + Gaussian view
   Carver cc, ct2;
   struct OffC {
-    size_t mean, cov, n, has, occ, gcell, g2c, table, cnt, segoff, cursor, gmask, gbase;
+    size_t mean, cov, n, has, occ, gcell, g2c, table, cnt, segoff, cursor, gmask, gbase, ckey;
   };
   std::vector<OffC> oc(L);
-  int max_ntb = 1;
+  int max_ntb = 1, max_cells = 1;
+  for (int l = 0; l < L; l++) {  // the hash tables first, contiguous: one memset initialises them all
+    int tsize = 2;
+    while (tsize < 2 * cnts[8 * l + 1]) tsize <<= 1;
+    live[l].tsize = tsize;
+    oc[l].table = cc.take(sizeof(HashEntry) * (size_t)tsize);
+  }
+  const size_t tables_bytes = cc.off;
   for (int l = 0; l < L; l++) {
     const int n_all = cnts[8 * l], ntb = cnts[8 * l + 1];
     max_ntb = std::max(max_ntb, ntb);
-    int tsize = 2;
-    while (tsize < 2 * ntb) tsize <<= 1;
+    max_cells = std::max(max_cells, n_all);
     live[l].n_all = n_all;
-    live[l].tsize = tsize;
     const size_t na = (size_t)std::max(n_all, 1);
     oc[l].mean = cc.take(24 * na), oc[l].cov = cc.take(72 * na), oc[l].n = cc.take(4 * na), oc[l].has = cc.take(4 * na);
     oc[l].occ = cc.take(4 * na), oc[l].gcell = cc.take(72 * na), oc[l].g2c = cc.take(4 * na);
-    oc[l].table = cc.take(sizeof(HashEntry) * (size_t)tsize);
-    oc[l].cnt = ct2.take(4 * na), oc[l].segoff = ct2.take(4 * na), oc[l].cursor = ct2.take(4 * na);
+    oc[l].cnt = ct2.take(4 * na), oc[l].segoff = ct2.take(4 * na), oc[l].cursor = ct2.take(4 * na), oc[l].ckey = ct2.take(4 * na);
     oc[l].gmask = ct2.take(8 * (size_t)std::max(ntb, 1)), oc[l].gbase = ct2.take(4 * (size_t)std::max(ntb, 1));
   }
   SlabP s_c, s_t2;
   if (int rc = slab_alloc(ctx, cc.off, s_c)) return rc;
   if (int rc = slab_alloc(ctx, ct2.off, s_t2)) return rc;
   CU_TRY(ctx, cudaMemsetAsync(s_t2->p, 0, s_t2->bytes, st));
+  CU_TRY(ctx, cudaMemsetAsync(s_c->p, 0xFF, tables_bytes, st));
   for (int l = 0; l < L; l++) {
     BuildJob &j = live[l];
     j.cmean = (double *)(s_c->p + oc[l].mean), j.ccov = (double *)(s_c->p + oc[l].cov);
@@ -367,14 +407,17 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     j.table = (HashEntry *)(s_c->p + oc[l].table);
     j.cnt = (int *)(s_t2->p + oc[l].cnt), j.seg_off = (int *)(s_t2->p + oc[l].segoff), j.cursor = (int *)(s_t2->p + oc[l].cursor);
     j.gmask_t = (unsigned long long *)(s_t2->p + oc[l].gmask), j.gbase_t = (int *)(s_t2->p + oc[l].gbase);
-    CU_TRY(ctx, cudaMemsetAsync(j.table, 0xFF, sizeof(HashEntry) * (size_t)j.tsize, st));
+    j.cell_key = (int *)(s_t2->p + oc[l].ckey);
   }
   CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
-  ctx->launches += launch_cells(d_jobs, L, max_pts, max_ntb, st);
+  pt.mark("alloc C");
+  ctx->launches += launch_cells(d_jobs, L, max_pts, max_ntb, max_cells, st);
+  pt.mark("cells");
   ctx->launches += launch_gview(d_jobs, L, max_ntb, st);
-  for (int l = 0; l < L; l++)
-    CU_TRY(ctx, cudaMemcpyAsync(&cnts[8 * l], live[l].counts, 32, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
+  for (int l = 0; l < L; l++) std::memcpy(&cnts[8 * l], &cnts_all[8 * (size_t)live_idx[l]], 32);
+  pt.mark("gview");
   for (int l = 0; l < L; l++) {
     ndtb_map *m = maps[live_idx[l]];
     const BuildJob &j = live[l];
@@ -385,6 +428,9 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     m->cmean = j.cmean, m->ccov = j.ccov, m->cn = j.cn, m->chas = j.chas, m->cocc = j.cocc;
     m->gcell = j.gcell, m->g2c = j.g2c, m->table = j.table, m->tsize = j.tsize;
   }
+  pt.mark("publish");
+  s_t.reset(), s_t2.reset(), s_jobs.reset(), keep_old.clear();
+  pt.mark("free temps");
   return NDTB_OK;
 }
 
@@ -466,6 +512,14 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
   const size_t o_goff = c.take(8 * n), o_gt = c.take(with_cov ? 48 * gt_total : 0);
   const size_t o_part = c.take(with_cov ? 8 * (size_t)cov_partial_width() * n_chunks * n : 0);
   const size_t o_cov = c.take(with_cov ? 288 * (size_t)n : 0), o_stat = c.take(4 * n);
+  // cluster width and straggler policy.  A registration that does not converge runs ITR_MAX iterations, ~5x the mean
+  // work: with one CTA per registration a handful of them would set the kernel time of a whole batch, so in large
+  // batches every registration gets a pass budget and the unfinished ones are completed on 8-CTA clusters.
+  const int sms = std::max(ctx->sm_count, 1);
+  auto pow2_floor = [](int v) { int p = 1; while (2 * p <= v) p <<= 1; return p; };
+  int G1 = p->ctas_per_match > 0 ? pow2_floor(std::min(p->ctas_per_match, 8)) : ((int64_t)2 * n >= sms ? 1 : pow2_floor((int)std::min<int64_t>(8, sms / n)));
+  int budget = p->pass_budget > 0 ? p->pass_budget : (p->pass_budget < 0 ? 0 : (((int64_t)n * G1 >= sms) ? 64 : 0));
+  const size_t o_states = c.take(budget > 0 ? opt_state_bytes() * (size_t)n : 0), o_unf = c.take(4 * (size_t)(n + 1));
   SlabP s;
   if (int rc = slab_alloc(ctx, c.off, s)) return rc;
   MatchJob *d_jobs = (MatchJob *)(s->p + o_jobs);
@@ -477,8 +531,20 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
     CU_TRY(ctx, cudaEventCreate(&ev1));
     CU_TRY(ctx, cudaEventRecord(ev0, st));
   }
-  CU_TRY(ctx, launch_match(d_jobs, (int)n, cfg, d_res, st));
+  int *d_unf = (int *)(s->p + o_unf);
+  if (budget > 0) CU_TRY(ctx, cudaMemsetAsync(d_unf, 0, 4, st));
+  CU_TRY(ctx, launch_match(d_jobs, nullptr, (int)n, G1, cfg, d_res, s->p + o_states, 0, budget, d_unf, st));
   ctx->launches += 1;
+  if (budget > 0) {
+    int n_unf = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&n_unf, d_unf, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (n_unf > 0) {
+      const int G2 = pow2_floor(std::min(8, std::max(1, sms / n_unf)));
+      CU_TRY(ctx, launch_match(d_jobs, d_unf + 1, n_unf, G2, cfg, d_res, s->p + o_states, 1, 0, d_unf, st));
+      ctx->launches += 1;
+    }
+  }
   if (ctx->timing) {
     CU_TRY(ctx, cudaEventRecord(ev1, st));
     ctx->timed.push_back({ev0, ev1});
@@ -596,7 +662,7 @@ void ndtb_default_params(ndtb_params *p) {
   p->use_soft_constraints = 0;
   p->use_tikhonov = 0;
   p->ctas_per_match = 0;
-  p->pad_ = 0;
+  p->pass_budget = 0;
 }
 
 // ---- maps
@@ -744,7 +810,10 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
   }
   std::vector<char> load((size_t)n_maps, 1);
   std::vector<double> range((size_t)n_maps, range_limit);
-  return build_batch(ctx, mv, ps, load, range, maxnumpoints, occupancy_limit);
+  PhaseTimer pt(ctx, "map_build_batch");
+  const int rc = build_batch(ctx, mv, ps, load, range, maxnumpoints, occupancy_limit);
+  pt.mark("build_batch");
+  return rc;
 }
 
 int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells, int64_t n, int use_idx) {
@@ -967,6 +1036,7 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
   if (!ctx || n_pairs < 0 || !p || !(cell > 0)) return NDTB_ERR_ARG;
   if (n_pairs == 0) return NDTB_OK;
   if (!tgt_pts || !n_tgt || !src_pts || !n_src || !T0s || !res) return NDTB_ERR_ARG;
+  PhaseTimer pt0(ctx, "register_scans");
   std::vector<std::unique_ptr<ndtb_map>> own((size_t)(2 * n_pairs));
   std::vector<ndtb_map *> maps((size_t)(2 * n_pairs));
   std::vector<const float *> pts((size_t)(2 * n_pairs));
@@ -984,14 +1054,18 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
     pts[i] = (i & 1) ? src_pts[e] : tgt_pts[e];
     npts[i] = (i & 1) ? n_src[e] : n_tgt[e];
   }
+  pt0.mark("create maps");
+  PhaseTimer pt(ctx, "register_scans");
   if (int rc = ndtb_map_build_batch(ctx, 2 * n_pairs, maps.data(), pts.data(), npts.data(), range_limit, in_mem, 0xffffffffu, 255.f))
     return rc;
+  pt.mark("build_batch");
   std::vector<const ndtb_map *> tg((size_t)n_pairs), sr((size_t)n_pairs);
   for (int64_t e = 0; e < n_pairs; e++) {
     tg[e] = maps[2 * e], sr[e] = maps[2 * e + 1];
     if (!maps[2 * e]->grid_ready || !maps[2 * e + 1]->grid_ready) return NDTB_ERR_EMPTY;
   }
   const int rc = match_batch_impl(ctx, n_pairs, tg.data(), sr.data(), T0s, nullptr, p, with_covariance && cov36s, out_mem, res, cov36s);
+  pt.mark("match+cov");
   if (rc == NDTB_OK && out_mem == NDTB_MEM_DEVICE) {
     // outputs stay on the device and the temporary maps are released stream-ordered: no host sync needed
   }

@@ -23,9 +23,16 @@ namespace cg = cooperative_groups;
 
 namespace ndtb {
 
-constexpr int MATCH_THREADS = 256;
+#ifndef NDTB_MATCH_THREADS
+#define NDTB_MATCH_THREADS 256
+#endif
+#ifndef NDTB_PUSH_SCAN
+#define NDTB_PUSH_SCAN 1  // 1: one warp prefix scan per probe column; 0: one ballot per pushed hit
+#endif
+constexpr int MATCH_THREADS = NDTB_MATCH_THREADS;
 constexpr int MATCH_WARPS = MATCH_THREADS / 32;
-constexpr int QCAP = 128;       // per-warp pair queue capacity (entries); >= 64
+constexpr int QCAP = 256;       // per-warp pair queue capacity (entries); >= 64
+constexpr int MAXSPAN = 3;      // 4-blocks per axis touched by a (2k+1)-voxel probe window, k <= 4
 constexpr int ACC_PAIRS = 28;   // slot counting contributing pairs
 constexpr int ACC_TOTAL = 29;
 constexpr unsigned FULL = 0xffffffffu;
@@ -156,6 +163,76 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
         const int by = by0 + dy;
         const bool oky = okx && by <= by1 && by >= 0 && by < nb1;
         const unsigned long long mxy = mx & expand_y(axis_bits(iy, k, by));
+#if NDTB_PUSH_SCAN
+        // one column of probes (all z-blocks): look up, count, one warp scan, every lane writes its own hits
+        unsigned long long hitsv[MAXSPAN], bmaskv[MAXSPAN];
+        int basev[MAXSPAN];
+        int cnt = 0;
+#pragma unroll
+        for (int dz = 0; dz < MAXSPAN; dz++) {
+          hitsv[dz] = 0ull, bmaskv[dz] = 0ull, basev[dz] = 0;
+          const int bz = bz0 + dz;
+          if (dz < span && oky && bz <= bz1 && bz >= 0 && bz < nb2) {
+            if (table_find(c.table, c.tsize, (bx * nb1 + by) * nb2 + bz, basev[dz], bmaskv[dz]))
+              hitsv[dz] = bmaskv[dz] & mxy & expand_z(axis_bits(iz, k, bz));
+          }
+          cnt += __popcll(hitsv[dz]);
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(FULL, incl, off);
+          if (lane >= off) incl += t;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total == 0) continue;
+        if (qcount + total > QCAP) {  // make room: drain the full batches
+          __syncwarp();
+          while (qcount >= 32) {
+            qcount -= 32;
+            process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
+          }
+          __syncwarp();
+        }
+        if (qcount + total <= QCAP) {
+          int pos = qcount + incl - cnt;
+#pragma unroll
+          for (int dz = 0; dz < MAXSPAN; dz++) {
+            unsigned long long hits = hitsv[dz];
+            while (hits) {
+              const int b = __ffsll((long long)hits) - 1;
+              hits &= hits - 1ull;
+              ws.queue[pos++] = ((unsigned)lane << 27) | (unsigned)(basev[dz] + __popcll(bmaskv[dz] & ((1ull << b) - 1ull)));
+            }
+          }
+          qcount += total;
+        } else {
+          // a column with more hits than the queue holds (very dense maps): one hit per lane per iteration
+#pragma unroll
+          for (int dz = 0; dz < MAXSPAN; dz++) {
+            unsigned long long hits = hitsv[dz];
+            for (;;) {
+              const unsigned active = __ballot_sync(FULL, hits != 0ull);
+              if (!active) break;
+              if (qcount + 32 > QCAP) {
+                __syncwarp();
+                while (qcount >= 32) {
+                  qcount -= 32;
+                  process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
+                }
+                __syncwarp();
+              }
+              if (hits) {
+                const int b = __ffsll((long long)hits) - 1;
+                hits &= hits - 1ull;
+                ws.queue[qcount + __popc(active & lt)] =
+                    ((unsigned)lane << 27) | (unsigned)(basev[dz] + __popcll(bmaskv[dz] & ((1ull << b) - 1ull)));
+              }
+              qcount += __popc(active);
+            }
+          }
+        }
+#else
         for (int dz = 0; dz < span; dz++) {
           const int bz = bz0 + dz;
           unsigned long long hits = 0, bmask = 0;
@@ -185,6 +262,7 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
             qcount += __popc(active);
           }
         }
+#endif
       }
     }
     // end of round: the staged cells are about to be overwritten — drain everything
@@ -258,27 +336,54 @@ __device__ __forceinline__ void stage_table_bulk(HashEntry *dst, const HashEntry
 }
 
 // ------------------------------------------------------------------ K5: whole registration in one launch
+constexpr int MAX_CLUSTER = 8;  // portable thread-block-cluster size limit
+
+struct MatchCtl {  // what every CTA of a registration's cluster needs to start the next pass
+  double P[12];    // pose of the pending evaluation: R row-major, t
+  int phase;       // PH_* of the optimiser, or PH_YIELD
+  int want_hess;
+};
+constexpr int PH_YIELD = 100;  // pass budget exhausted: state saved, the registration continues in a later launch
+
 struct MatchShared {
-  OptState st;
+  OptState st;  // rank 0 only
   OptParams prm;
   GridDesc grid;
-  double P[12];  // pose of the pending evaluation: R row-major, t
+  MatchCtl ctl;
   double sums[ACC_TOTAL];
+  double csums[MAX_CLUSTER][ACC_TOTAL];  // rank 0 only: per-CTA partial sums written through DSMEM
   double red[MATCH_WARPS * ACC_TOTAL];
-  double pairs_last;
   uint64_t mbar;
 };
 
 extern __shared__ __align__(16) unsigned char dyn_smem[];
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One registration per thread-block CLUSTER (G = 1..8 CTAs).  Every pass is split over the G*MATCH_WARPS warps;
+// the per-CTA sums go to rank 0 through distributed shared memory, rank 0's thread 0 advances the optimiser and
+// broadcasts the next pose the same way.  job_ids (optional) selects the jobs of this launch; states/pass_budget
+// implement the straggler hand-over: a registration that has used pass_budget derivative passes saves its optimiser
+// state and is finished by a second launch with a wider cluster.
 __global__ void __launch_bounds__(MATCH_THREADS, 1)
-match_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, ndtb_result *__restrict__ out) {
+match_kernel(const MatchJob *__restrict__ jobs, const int *__restrict__ job_ids, MatchConfig cfg, ndtb_result *__restrict__ out,
+             OptState *__restrict__ states, int resume, int pass_budget, int *__restrict__ unfinished /*[0]=count, ids follow*/) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned G = cluster.num_blocks();
+  const unsigned rank = cluster.block_rank();
   // dynamic smem: [table staging][MatchShared][WarpScratch x warps]
   HashEntry *stab = reinterpret_cast<HashEntry *>(dyn_smem);
   MatchShared &sh = *reinterpret_cast<MatchShared *>(dyn_smem + (size_t)cfg.table_smem_entries * sizeof(HashEntry));
   WarpScratch *wsp = reinterpret_cast<WarpScratch *>(reinterpret_cast<unsigned char *>(&sh) + ((sizeof(MatchShared) + 15) & ~(size_t)15));
-  const MatchJob &job = jobs[blockIdx.x];
+  const int slot = blockIdx.x / G;
+  const int jid = job_ids ? job_ids[slot] : slot;
+  const MatchJob &job = jobs[jid];
   const int warp = threadIdx.x >> 5;
+  const unsigned long long t_start = globaltimer_ns();
 
   PassCtx c;
   c.g = &sh.grid;
@@ -291,54 +396,96 @@ match_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, ndtb_result *__
   const bool staged = job.tgt.tsize <= cfg.table_smem_entries;
   c.table = staged ? stab : job.tgt.table;
 
+  if (G > 1) cluster.sync();  // every CTA of the cluster has started: its shared memory may be written remotely
   if (threadIdx.x == 0) {
     sh.grid = job.tgt.g;
-    OptParams &p = sh.prm;
-    p.itr_max = cfg.itr_max, p.step_control = cfg.step_control, p.regularize = cfg.regularize;
-    p.fusion = job.fusion, p.soft = job.fusion && cfg.soft, p.tik = job.fusion && cfg.tik;
-    p.delta_score = cfg.delta_score;
-    for (int i = 0; i < 36; i++) p.Q[i] = job.Q[i];
-    opt_begin(sh.st, p, job.T0);
-    for (int i = 0; i < 9; i++) sh.P[i] = sh.st.Peval.R[i];
-    for (int i = 0; i < 3; i++) sh.P[9 + i] = sh.st.Peval.t[i];
+    if (rank == 0) {
+      OptParams &p = sh.prm;
+      p.itr_max = cfg.itr_max, p.step_control = cfg.step_control, p.regularize = cfg.regularize;
+      p.fusion = job.fusion, p.soft = job.fusion && cfg.soft, p.tik = job.fusion && cfg.tik;
+      p.delta_score = cfg.delta_score;
+      for (int i = 0; i < 36; i++) p.Q[i] = job.Q[i];
+      if (resume)
+        sh.st = states[jid];
+      else
+        opt_begin(sh.st, p, job.T0);
+      MatchCtl ctl;
+      for (int i = 0; i < 9; i++) ctl.P[i] = sh.st.Peval.R[i];
+      for (int i = 0; i < 3; i++) ctl.P[9 + i] = sh.st.Peval.t[i];
+      ctl.phase = sh.st.phase, ctl.want_hess = sh.st.want_hess;
+      for (unsigned r = 0; r < G; r++) *cluster.map_shared_rank(&sh.ctl, r) = ctl;
+    }
   }
   if (staged)
     stage_table_bulk(stab, job.tgt.table, job.tgt.tsize, &sh.mbar);
-  __syncthreads();
+  if (G > 1)
+    cluster.sync();
+  else
+    __syncthreads();
 
+  int passes = 0;
   for (;;) {
-    if (sh.st.phase == PH_DONE) break;  // uniform: shared state, read after a barrier
-    const bool hess = sh.st.want_hess != 0;
+    const int phase = sh.ctl.phase;  // uniform over the cluster: written before the last barrier
+    if (phase == PH_DONE || phase == PH_YIELD) break;
+    const bool hess = sh.ctl.want_hess != 0;
     double acc[ACC_TOTAL];
 #pragma unroll
     for (int j = 0; j < ACC_TOTAL; j++) acc[j] = 0.0;
     if (hess)
-      d2d_pass<true>(c, sh.P, wsp[warp], warp, MATCH_WARPS, acc);
+      d2d_pass<true>(c, sh.ctl.P, wsp[warp], rank * MATCH_WARPS + warp, G * MATCH_WARPS, acc);
     else
-      d2d_pass<false>(c, sh.P, wsp[warp], warp, MATCH_WARPS, acc);
+      d2d_pass<false>(c, sh.ctl.P, wsp[warp], rank * MATCH_WARPS + warp, G * MATCH_WARPS, acc);
     block_reduce(acc, hess ? 28 : 7, sh.red, sh.sums, MATCH_WARPS);
-    if (threadIdx.x == 0) {
-      opt_advance(sh.st, sh.prm, sh.sums);
-      for (int i = 0; i < 9; i++) sh.P[i] = sh.st.Peval.R[i];
-      for (int i = 0; i < 3; i++) sh.P[9 + i] = sh.st.Peval.t[i];
+    passes++;
+    if (G > 1) {
+      if (threadIdx.x < ACC_TOTAL) cluster.map_shared_rank(&sh.csums[0][0], 0)[rank * ACC_TOTAL + threadIdx.x] = sh.sums[threadIdx.x];
+      cluster.sync();
     }
-    __syncthreads();
+    if (rank == 0 && threadIdx.x == 0) {
+      if (G > 1)
+        for (int j = 0; j < ACC_TOTAL; j++) {
+          double v = 0.0;
+          for (unsigned r = 0; r < G; r++) v += sh.csums[r][j];  // fixed order: deterministic
+          sh.sums[j] = v;
+        }
+      opt_advance(sh.st, sh.prm, sh.sums);
+      MatchCtl ctl;
+      for (int i = 0; i < 9; i++) ctl.P[i] = sh.st.Peval.R[i];
+      for (int i = 0; i < 3; i++) ctl.P[9 + i] = sh.st.Peval.t[i];
+      ctl.phase = sh.st.phase, ctl.want_hess = sh.st.want_hess;
+      if (ctl.phase != PH_DONE && pass_budget > 0 && passes >= pass_budget) ctl.phase = PH_YIELD;
+      for (unsigned r = 0; r < G; r++) *cluster.map_shared_rank(&sh.ctl, r) = ctl;
+    }
+    if (G > 1)
+      cluster.sync();
+    else
+      __syncthreads();
   }
 
-  if (threadIdx.x == 0) {
+  if (rank == 0 && threadIdx.x == 0) {
     const OptState &s = sh.st;
-    ndtb_result r;
-    pose_to_cm(s.T, r.T);
-    r.score = s.score_here, r.score_best = s.score_best;
-    r.converged = s.ret, r.iterations = s.itr, r.n_hess_passes = s.n_hess, r.n_grad_passes = s.n_grad;
-    r.exit_code = s.exit_code;
-    int changed = 0;
-    for (int i = 0; i < 16; i++) changed |= (r.T[i] != job.T0[i]);
-    r.pose_changed = changed;
-    r.status = (s.ret ? NDTB_ST_CONVERGED : NDTB_ST_ITR_MAX) | (changed ? NDTB_ST_POSE_CHANGED : 0) |
-               (s.nonfinite ? NDTB_ST_NONFINITE : 0) | ((job.src_ng == 0 || job.tgt.ng == 0) ? NDTB_ST_NO_CELLS : 0);
-    r.n_src_cells = job.src_ng, r.n_tgt_cells = job.tgt.ng, r.tgt_table_entries = job.tgt.tsize;
-    out[blockIdx.x] = r;
+    const float ms = (float)((double)(globaltimer_ns() - t_start) * 1e-6);
+    if (sh.ctl.phase == PH_YIELD) {
+      states[jid] = s;
+      out[jid].kernel_ms = ms;  // carried over to the finishing launch
+      const int at = atomicAdd(unfinished, 1);
+      unfinished[1 + at] = jid;
+    } else {
+      ndtb_result r;
+      pose_to_cm(s.T, r.T);
+      r.score = s.score_here, r.score_best = s.score_best;
+      r.converged = s.ret, r.iterations = s.itr, r.n_hess_passes = s.n_hess, r.n_grad_passes = s.n_grad;
+      r.exit_code = s.exit_code;
+      int changed = 0;
+      for (int i = 0; i < 16; i++) changed |= (r.T[i] != job.T0[i]);
+      r.pose_changed = changed;
+      r.status = (s.ret ? NDTB_ST_CONVERGED : NDTB_ST_ITR_MAX) | (changed ? NDTB_ST_POSE_CHANGED : 0) |
+                 (s.nonfinite ? NDTB_ST_NONFINITE : 0) | ((job.src_ng == 0 || job.tgt.ng == 0) ? NDTB_ST_NO_CELLS : 0);
+      r.n_src_cells = job.src_ng, r.n_tgt_cells = job.tgt.ng, r.tgt_table_entries = job.tgt.tsize;
+      r.kernel_ms = ms * (float)G + (resume ? out[jid].kernel_ms : 0.f);  // SM-milliseconds spent on this registration
+      r.n_exec_passes = s.n_exec;
+      out[jid] = r;
+    }
   }
 }
 
@@ -346,29 +493,42 @@ size_t match_smem_bytes(int table_entries) {
   return (size_t)table_entries * sizeof(HashEntry) + ((sizeof(MatchShared) + 15) & ~(size_t)15) +
          MATCH_WARPS * sizeof(WarpScratch);
 }
+size_t opt_state_bytes() { return sizeof(OptState); }
 
-cudaError_t launch_match(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, ndtb_result *d_out,
+// n_slots registrations (job_ids[slot] or slot itself), each on a cluster of `cluster` CTAs
+cudaError_t launch_match(const MatchJob *d_jobs, const int *d_job_ids, int n_slots, int cluster, const MatchConfig &cfg,
+                         ndtb_result *d_out, void *d_states, int resume, int pass_budget, int *d_unfinished,
                          cudaStream_t stream) {
   const size_t smem = match_smem_bytes(cfg.table_smem_entries);
   cudaError_t e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  match_kernel<<<n_jobs, MATCH_THREADS, smem, stream>>>(d_jobs, cfg, d_out);
-  return cudaGetLastError();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)(n_slots * cluster));
+  lc.blockDim = dim3(MATCH_THREADS);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  lc.attrs = at, lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, match_kernel, d_jobs, d_job_ids, cfg, d_out, (OptState *)d_states, resume, pass_budget,
+                            d_unfinished);
 }
 
 // ------------------------------------------------------------------ stand-alone derivativesNDT (API + tests)
+constexpr int DERIV_WARPS = 8;
 struct DerivShared {
   GridDesc grid;
   double P[12];
   double sums[ACC_TOTAL];
-  double red[MATCH_WARPS * ACC_TOTAL];
+  double red[DERIV_WARPS * ACC_TOTAL];
 };
 
 template <bool HESS>
-__global__ void __launch_bounds__(MATCH_THREADS, 1)
+__global__ void __launch_bounds__(DERIV_WARPS * 32, 1)
 deriv_kernel(const MatchJob *__restrict__ job_p, MatchConfig cfg, double *__restrict__ partial /*[grid][ACC_TOTAL]*/) {
   __shared__ DerivShared sh;
-  __shared__ WarpScratch ws[MATCH_WARPS];
+  __shared__ WarpScratch ws[DERIV_WARPS];
   const MatchJob &job = *job_p;
   if (threadIdx.x == 0) {
     sh.grid = job.tgt.g;
@@ -386,8 +546,8 @@ deriv_kernel(const MatchJob *__restrict__ job_p, MatchConfig cfg, double *__rest
 #pragma unroll
   for (int j = 0; j < ACC_TOTAL; j++) acc[j] = 0.0;
   const int warp = threadIdx.x >> 5;
-  d2d_pass<HESS>(c, sh.P, ws[warp], blockIdx.x * MATCH_WARPS + warp, gridDim.x * MATCH_WARPS, acc);
-  block_reduce(acc, HESS ? 28 : 7, sh.red, sh.sums, MATCH_WARPS);
+  d2d_pass<HESS>(c, sh.P, ws[warp], blockIdx.x * DERIV_WARPS + warp, gridDim.x * DERIV_WARPS, acc);
+  block_reduce(acc, HESS ? 28 : 7, sh.red, sh.sums, DERIV_WARPS);
   if (threadIdx.x < ACC_TOTAL) partial[blockIdx.x * ACC_TOTAL + threadIdx.x] = sh.sums[threadIdx.x];
 }
 
@@ -402,9 +562,9 @@ __global__ void sum_partials_kernel(const double *__restrict__ partial, int n_pa
 cudaError_t launch_derivatives(const MatchJob *d_job, const MatchConfig &cfg, bool hess, int n_ctas, double *d_partial,
                                double *d_out29, cudaStream_t stream) {
   if (hess)
-    deriv_kernel<true><<<n_ctas, MATCH_THREADS, 0, stream>>>(d_job, cfg, d_partial);
+    deriv_kernel<true><<<n_ctas, DERIV_WARPS * 32, 0, stream>>>(d_job, cfg, d_partial);
   else
-    deriv_kernel<false><<<n_ctas, MATCH_THREADS, 0, stream>>>(d_job, cfg, d_partial);
+    deriv_kernel<false><<<n_ctas, DERIV_WARPS * 32, 0, stream>>>(d_job, cfg, d_partial);
   sum_partials_kernel<<<1, 32, 0, stream>>>(d_partial, n_ctas, ACC_TOTAL, d_out29);
   return cudaGetLastError();
 }

@@ -36,27 +36,29 @@ __global__ void k_centroid(const BuildJob *__restrict__ jobs, const int *__restr
   const int lane = threadIdx.x;
   double sx = 0, sy = 0, sz = 0;
   long long cnt = 0;
+  // the sums must be taken in point order (each addition rounds): 32 points are fetched coalesced one chunk
+  // ahead, converted to double by their own lane, then broadcast one after the other
+  float4 nxt = make_float4(0, 0, 0, 0);
+  if (lane < j.npts) nxt = j.pts[lane];
   for (int base = 0; base < j.npts; base += 32) {
+    const float4 p = nxt;
     const int i = base + lane;
-    float4 p = make_float4(0, 0, 0, 0);
-    bool use = false;
-    if (i < j.npts) {
-      p = j.pts[i];
-      use = !pt_skip(p, j.range_limit);
-    }
+    if (i + 32 < j.npts) nxt = j.pts[i + 32];
+    const bool use = i < j.npts && !pt_skip(p, j.range_limit);
+    const double dx = (double)p.x, dy = (double)p.y, dz = (double)p.z;
     const unsigned m = __ballot_sync(FULL, use);
     if (m == FULL) {
 #pragma unroll
       for (int r = 0; r < 32; r++) {
-        sx += (double)__shfl_sync(FULL, p.x, r);
-        sy += (double)__shfl_sync(FULL, p.y, r);
-        sz += (double)__shfl_sync(FULL, p.z, r);
+        sx += __shfl_sync(FULL, dx, r);
+        sy += __shfl_sync(FULL, dy, r);
+        sz += __shfl_sync(FULL, dz, r);
       }
       cnt += 32;
     } else {
       for (int r = 0; r < 32; r++) {
-        const float x = __shfl_sync(FULL, p.x, r), y = __shfl_sync(FULL, p.y, r), z = __shfl_sync(FULL, p.z, r);
-        if (m >> r & 1u) sx += (double)x, sy += (double)y, sz += (double)z, cnt++;
+        const double x = __shfl_sync(FULL, dx, r), y = __shfl_sync(FULL, dy, r), z = __shfl_sync(FULL, dz, r);
+        if (m >> r & 1u) sx += x, sy += y, sz += z, cnt++;
       }
     }
   }
@@ -205,7 +207,7 @@ __global__ void k_scatter(const BuildJob *__restrict__ jobs) {
 // NDTCell::rescaleCovariance [upstream]: any eigenvalue <= 0 -> no Gaussian; clamp to >= max/1000 (fixture-pinned)
 __device__ bool rescale_covariance(double *cov) {
   double ev[3], V[9];
-  eig_sym(3, cov, ev, V);
+  eig_sym_n<3>(cov, ev, V);
   if (ev[0] <= 0 || ev[1] <= 0 || ev[2] <= 0) return false;
   double maxe = ev[0] > ev[1] ? ev[0] : ev[1];
   maxe = maxe > ev[2] ? maxe : ev[2];
@@ -222,111 +224,130 @@ __device__ bool rescale_covariance(double *cov) {
   return true;
 }
 
-// one warp per touched block; its cells are processed one after another; every lane computes the same
-// sequential sums (points are fetched 32 at a time, coalesced by the gather, then broadcast by shuffles)
-__global__ void __launch_bounds__(256) k_cells(const BuildJob *__restrict__ jobs) {
+// (a) one warp per touched block: record every cell's voxel key and sort its point ids ascending
+// (= insertion order of NDTCell::points_): shuffle ranking for n <= 32, bitonic network in shared memory up to
+// SORT_CAP, counting ranks beyond.
+constexpr int SORT_CAP = 1024;
+
+__global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restrict__ jobs) {
+  __shared__ int sbuf[8][SORT_CAP];
   const BuildJob &j = jobs[blockIdx.y];
   const int lane = threadIdx.x & 31;
+  int *sb = sbuf[threadIdx.x >> 5];
   const int ntb = j.counts[1];
   for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ntb; t += gridDim.x * 8) {
     const int b = j.tb_list[t];
     unsigned long long m = j.amask[b];
-    const unsigned long long om = j.o_amask ? j.o_amask[b] : 0ull;
     int c = j.abase[b];
     for (; m; m &= m - 1ull, c++) {
-      const int bit = __ffsll((long long)m) - 1;
-      // previous record
-      double mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      int N = 0, has = 0;
-      float occ = 0.f;
+      if (lane == 0) j.cell_key[c] = b * 64 + (__ffsll((long long)m) - 1);
+      const int n = j.cnt[c];
+      if (n == 0) continue;
+      const int *seg = j.seg_idx + j.seg_off[c];
+      int *srt = j.seg2 + j.seg_off[c];
+      if (n <= 32) {
+        const int v = lane < n ? seg[lane] : 0x7fffffff;
+        int r = 0;
+        for (int q = 0; q < n; q++) r += __shfl_sync(FULL, v, q) < v;
+        if (lane < n) srt[r] = v;
+      } else if (n <= SORT_CAP) {
+        int mm = 64;
+        while (mm < n) mm <<= 1;
+        for (int e = lane; e < mm; e += 32) sb[e] = e < n ? seg[e] : 0x7fffffff;
+        __syncwarp();
+        for (int k = 2; k <= mm; k <<= 1)
+          for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int tt = lane; tt < (mm >> 1); tt += 32) {
+              const int i0 = 2 * tt - (tt & (jj - 1)), i1 = i0 + jj;
+              const int a0 = sb[i0], a1 = sb[i1];
+              const bool up = (i0 & k) == 0;
+              if ((a0 > a1) == up) sb[i0] = a1, sb[i1] = a0;
+            }
+            __syncwarp();
+          }
+        for (int e = lane; e < n; e += 32) srt[e] = sb[e];
+        __syncwarp();
+      } else {
+        for (int e = lane; e < n; e += 32) {
+          const int v = seg[e];
+          int r = 0;
+          for (int q = 0; q < n; q++) r += seg[q] < v;
+          srt[r] = v;
+        }
+      }
+    }
+  }
+}
+
+// (b) one THREAD per cell: sequential mean and scatter matrix over its points in id order (the operation order of
+// NDTCell::computeGaussian), merge with the stored (N, mean, cov), occupancy, eigen clamp.
+__global__ void __launch_bounds__(128) k_cells(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < j.n_all; c += gridDim.x * blockDim.x) {
+    const int key = j.cell_key[c];
+    const int b = key >> 6, bit = key & 63;
+    double mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int N = 0, has = 0;
+    float occ = 0.f;
+    if (j.o_amask) {  // previous record of this voxel
+      const unsigned long long om = j.o_amask[b];
       if (om >> bit & 1ull) {
         const int oc = j.o_abase[b] + __popcll(om & ((1ull << bit) - 1ull));
         for (int q = 0; q < 3; q++) mean[q] = j.o_cmean[(size_t)oc * 3 + q];
         for (int q = 0; q < 9; q++) cov[q] = j.o_ccov[(size_t)oc * 9 + q];
         N = j.o_cn[oc], has = j.o_chas[oc], occ = j.o_cocc[oc];
       }
-      const int n = j.cnt[c];
-      if (n > 0) {
-        int *seg = j.seg_idx + j.seg_off[c];
-        int *srt = j.seg2 + j.seg_off[c];
-        // rank-sort the point ids (ascending = insertion order of NDTCell::points_)
-        if (n <= 32) {
-          const int v = lane < n ? seg[lane] : 0x7fffffff;
-          int r = 0;
-          for (int q = 0; q < n; q++) r += __shfl_sync(FULL, v, q) < v;
-          if (lane < n) srt[r] = v;
-        } else {
-          for (int e = lane; e < n; e += 32) {
-            const int v = seg[e];
-            int r = 0;
-            for (int q = 0; q < n; q++) r += seg[q] < v;
-            srt[r] = v;
-          }
-        }
-        __syncwarp();
-        // occupancy: += n*log(0.6/0.4), clamped (NDTCell::updateOccupancy)
-        {
-          float o2 = occ + (float)((double)n * j.log_occ);
-          o2 = o2 > j.occ_limit ? j.occ_limit : o2;
-          o2 = o2 < -j.occ_limit ? -j.occ_limit : o2;
-          occ = o2;
-        }
-        if (has || n >= 3) {
-          double ms[3] = {0, 0, 0};
-          for (int base = 0; base < n; base += 32) {
-            const int cntc = n - base < 32 ? n - base : 32;
-            float4 p = make_float4(0, 0, 0, 0);
-            if (lane < cntc) p = j.pts[srt[base + lane]];
-            for (int r = 0; r < cntc; r++) {
-              ms[0] += (double)__shfl_sync(FULL, p.x, r);
-              ms[1] += (double)__shfl_sync(FULL, p.y, r);
-              ms[2] += (double)__shfl_sync(FULL, p.z, r);
-            }
-          }
-          const double ml[3] = {ms[0] / (double)n, ms[1] / (double)n, ms[2] / (double)n};
-          double cs[6] = {0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz
-          for (int base = 0; base < n; base += 32) {
-            const int cntc = n - base < 32 ? n - base : 32;
-            float4 p = make_float4(0, 0, 0, 0);
-            if (lane < cntc) p = j.pts[srt[base + lane]];
-            for (int r = 0; r < cntc; r++) {
-              const double d0 = (double)__shfl_sync(FULL, p.x, r) - ml[0];
-              const double d1 = (double)__shfl_sync(FULL, p.y, r) - ml[1];
-              const double d2 = (double)__shfl_sync(FULL, p.z, r) - ml[2];
-              cs[0] += d0 * d0, cs[1] += d0 * d1, cs[2] += d0 * d2;
-              cs[3] += d1 * d1, cs[4] += d1 * d2, cs[5] += d2 * d2;
-            }
-          }
-          const double csum[9] = {cs[0], cs[1], cs[2], cs[1], cs[3], cs[4], cs[2], cs[4], cs[5]};
-          if (!has) {
-            for (int q = 0; q < 3; q++) mean[q] = ml[q];
-            for (int q = 0; q < 9; q++) cov[q] = csum[q] / (double)(n - 1);
-            N = n;
-          } else {  // pairwise (Chan) merge with the stored (N, mean, cov)
-            const double N0 = (double)N, n1 = (double)n;
-            double mS[3], cS[9], tv[3];
-            for (int q = 0; q < 3; q++) mS[q] = mean[q] * N0;
-            for (int q = 0; q < 9; q++) cS[q] = cov[q] * (N0 - 1.0);
-            const double w = N0 / (n1 * (N0 + n1));
-            for (int q = 0; q < 3; q++) tv[q] = (n1 / N0) * mS[q] - ms[q];
-            for (int a = 0; a < 3; a++)
-              for (int bb = 0; bb < 3; bb++) cS[a * 3 + bb] += csum[a * 3 + bb] + w * tv[a] * tv[bb];
-            for (int q = 0; q < 3; q++) mS[q] += ms[q];
-            double Nt = N0 + n1;
-            for (int q = 0; q < 3; q++) mean[q] = mS[q] / Nt;
-            for (int q = 0; q < 9; q++) cov[q] = cS[q] / (Nt - 1.0);
-            if (Nt > (double)j.maxnumpoints) Nt = (double)j.maxnumpoints;
-            N = (int)Nt;
-          }
-          has = rescale_covariance(cov) ? 1 : 0;
-        }
+    }
+    const int n = j.cnt[c];
+    if (n > 0) {
+      const int *ids = j.seg2 + j.seg_off[c];
+      {  // occupancy: += n*log(0.6/0.4), clamped (NDTCell::updateOccupancy)
+        float o2 = occ + (float)((double)n * j.log_occ);
+        o2 = o2 > j.occ_limit ? j.occ_limit : o2;
+        o2 = o2 < -j.occ_limit ? -j.occ_limit : o2;
+        occ = o2;
       }
-      if (lane == 0) {
-        for (int q = 0; q < 3; q++) j.cmean[(size_t)c * 3 + q] = mean[q];
-        for (int q = 0; q < 9; q++) j.ccov[(size_t)c * 9 + q] = cov[q];
-        j.cn[c] = N, j.chas[c] = has, j.cocc[c] = occ;
+      if (has || n >= 3) {
+        double ms0 = 0, ms1 = 0, ms2 = 0;
+        for (int q = 0; q < n; q++) {
+          const float4 p = j.pts[ids[q]];
+          ms0 += (double)p.x, ms1 += (double)p.y, ms2 += (double)p.z;
+        }
+        const double ml0 = ms0 / (double)n, ml1 = ms1 / (double)n, ml2 = ms2 / (double)n;
+        double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+        for (int q = 0; q < n; q++) {
+          const float4 p = j.pts[ids[q]];
+          const double d0 = (double)p.x - ml0, d1 = (double)p.y - ml1, d2 = (double)p.z - ml2;
+          c00 += d0 * d0, c01 += d0 * d1, c02 += d0 * d2, c11 += d1 * d1, c12 += d1 * d2, c22 += d2 * d2;
+        }
+        const double ms[3] = {ms0, ms1, ms2}, ml[3] = {ml0, ml1, ml2};
+        const double csum[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22};
+        if (!has) {
+          for (int q = 0; q < 3; q++) mean[q] = ml[q];
+          for (int q = 0; q < 9; q++) cov[q] = csum[q] / (double)(n - 1);
+          N = n;
+        } else {  // pairwise (Chan) merge with the stored (N, mean, cov)
+          const double N0 = (double)N, n1 = (double)n;
+          double mS[3], cS[9], tv[3];
+          for (int q = 0; q < 3; q++) mS[q] = mean[q] * N0;
+          for (int q = 0; q < 9; q++) cS[q] = cov[q] * (N0 - 1.0);
+          const double w = N0 / (n1 * (N0 + n1));
+          for (int q = 0; q < 3; q++) tv[q] = (n1 / N0) * mS[q] - ms[q];
+          for (int a = 0; a < 3; a++)
+            for (int bb = 0; bb < 3; bb++) cS[a * 3 + bb] += csum[a * 3 + bb] + w * tv[a] * tv[bb];
+          for (int q = 0; q < 3; q++) mS[q] += ms[q];
+          double Nt = N0 + n1;
+          for (int q = 0; q < 3; q++) mean[q] = mS[q] / Nt;
+          for (int q = 0; q < 9; q++) cov[q] = cS[q] / (Nt - 1.0);
+          if (Nt > (double)j.maxnumpoints) Nt = (double)j.maxnumpoints;
+          N = (int)Nt;
+        }
+        has = rescale_covariance(cov) ? 1 : 0;
       }
     }
+    for (int q = 0; q < 3; q++) j.cmean[(size_t)c * 3 + q] = mean[q];
+    for (int q = 0; q < 9; q++) j.ccov[(size_t)c * 9 + q] = cov[q];
+    j.cn[c] = N, j.chas[c] = has, j.cocc[c] = occ;
   }
 }
 
@@ -529,12 +550,13 @@ int launch_mark(const BuildJob *d_jobs, int n, int max_pts, cudaStream_t s) {
   k_blockscan<<<n, 1024, 0, s>>>(d_jobs);
   return 2;
 }
-int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, cudaStream_t s) {
+int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int max_cells, cudaStream_t s) {
   k_count<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
   k_segscan<<<n, 1024, 0, s>>>(d_jobs);
   k_scatter<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
-  k_cells<<<dim3(chunks_for(max_ntb, 8), n), 256, 0, s>>>(d_jobs);
-  return 4;
+  k_sort_segments<<<dim3(chunks_for(max_ntb, 8), n), 256, 0, s>>>(d_jobs);
+  k_cells<<<dim3(chunks_for(max_cells, 128), n), 128, 0, s>>>(d_jobs);
+  return 5;
 }
 int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s) {
   k_gscan<<<n, 1024, 0, s>>>(d_jobs);

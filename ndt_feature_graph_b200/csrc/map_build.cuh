@@ -25,6 +25,7 @@ struct BuildJob {
   // per-cell (valid after the popcount scan)
   int n_all;
   int *cnt, *seg_off, *cursor;
+  int *cell_key;  // [n_all] block*64+bit of every cell
   double *cmean;  // [n_all][3]
   double *ccov;   // [n_all][9]
   int *cn, *chas;
@@ -49,7 +50,7 @@ struct BuildJob {
 
 int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, double *d_out, cudaStream_t s);
 int launch_mark(const BuildJob *d_jobs, int n, int max_pts, cudaStream_t s);
-int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, cudaStream_t s);
+int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int max_cells, cudaStream_t s);
 int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s);
 int launch_blockscan(const BuildJob *d_jobs, int n, cudaStream_t s);
 int launch_export(const BuildJob *d_job, int ntb, ndtb_cell *d_out, cudaStream_t s);

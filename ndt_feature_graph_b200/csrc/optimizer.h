@@ -52,6 +52,14 @@ struct OptState {
   double X[6];
   double stp, dginit, dgtest, width, width1, finit, stx, fx, dgx, sty, fy, dgy, stmin, stmax;
   int infoc, nfev, brackt, stage1;
+  // evaluations the reference repeats at a pose it has just evaluated are answered from these (bitwise the same
+  // value a repeated pass would give): score + gradient of the Hessian pass at T (line-search start), and the pose /
+  // score of the last evaluation (final score when the last step lands on an evaluated trial pose)
+  double sg[7];
+  Pose Plast;
+  double score_last;
+  int have_last;
+  int n_exec;  // derivative passes actually executed on the device
 };
 
 // ------------------------------------------------------------------ small dense algebra
@@ -112,9 +120,11 @@ NDTB_HDF inline double robust_yaw(const Pose &P) {
   return P.R[3] > 0 ? a : -a;
 }
 
-// cyclic Jacobi, symmetric n x n (n<=6), eigenvalues ascending, eigenvectors in the columns of V
-NDTB_HDF inline void eig_sym(int n, const double *Ain, double *evals, double *V) {
-  double A[36];
+// cyclic Jacobi, symmetric n x n (n<=6), eigenvalues ascending, eigenvectors in the columns of V.
+// Compile-time n: every loop unrolls and the 3x3 instance (one per NDT cell) lives in registers.
+template <int n>
+NDTB_HDF inline void eig_sym_n(const double *Ain, double *evals, double *V) {
+  double A[n * n];
   for (int i = 0; i < n * n; i++) A[i] = Ain[i];
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
@@ -126,7 +136,13 @@ NDTB_HDF inline void eig_sym(int n, const double *Ain, double *evals, double *V)
         if (i == j) diag += a2; else off += a2;
       }
     if (off <= 1e-32 * diag || off == 0.0) break;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
     for (int p = 0; p < n - 1; p++)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
       for (int q = p + 1; q < n; q++) {
         const double apq = A[p * n + q];
         if (apq == 0.0) continue;
@@ -150,20 +166,31 @@ NDTB_HDF inline void eig_sym(int n, const double *Ain, double *evals, double *V)
         }
       }
   }
-  int order[6];
-  for (int i = 0; i < n; i++) order[i] = i;
-  for (int i = 1; i < n; i++) {  // stable insertion sort by eigenvalue
-    const int oi = order[i];
-    int j = i - 1;
-    while (j >= 0 && A[order[j] * n + order[j]] > A[oi * n + oi]) order[j + 1] = order[j], j--;
-    order[j + 1] = oi;
-  }
-  double Vt[36];
+  // stable ascending order by eigenvalue (selection network free of dynamic indexing for small n)
+  double d[n];
+  int order[n];
+  for (int i = 0; i < n; i++) d[i] = A[i * n + i], order[i] = i;
+  for (int i = 1; i < n; i++)
+    for (int k = i; k > 0; k--) {
+      if (d[k - 1] > d[k]) {
+        const double td = d[k - 1]; d[k - 1] = d[k]; d[k] = td;
+        const int to = order[k - 1]; order[k - 1] = order[k]; order[k] = to;
+      }
+    }
+  double Vt[n * n];
   for (int j = 0; j < n; j++) {
-    evals[j] = A[order[j] * n + order[j]];
-    for (int i = 0; i < n; i++) Vt[i * n + j] = V[i * n + order[j]];
+    evals[j] = d[j];
+    for (int i = 0; i < n; i++) {
+      double v = 0.0;
+      for (int o = 0; o < n; o++) v = (order[j] == o) ? V[i * n + o] : v;
+      Vt[i * n + j] = v;
+    }
   }
   for (int i = 0; i < n * n; i++) V[i] = Vt[i];
+}
+NDTB_HDF inline void eig_sym(int n, const double *Ain, double *evals, double *V) {
+  if (n == 3) eig_sym_n<3>(Ain, evals, V);
+  else eig_sym_n<6>(Ain, evals, V);
 }
 
 // x = A^-1 b, LDL^T with symmetric diagonal pivoting (Eigen::LDLT semantics), n = 6
@@ -358,6 +385,8 @@ NDTB_HDF inline void opt_begin(OptState &s, const OptParams &prm, const double *
   s.itr = 0, s.ret = 1, s.exit_code = 0, s.n_hess = 0, s.n_grad = 0, s.nonfinite = 0;
   for (int i = 0; i < 6; i++) s.pose_local[i] = s.x0[i] = s.incr[i] = s.scg[i] = s.X[i] = 0.0;
   s.ls_soft = 0;
+  s.have_last = 0, s.n_exec = 0, s.score_last = 0;
+  for (int i = 0; i < 7; i++) s.sg[i] = 0.0;
   opt_request(s, s.T, 1, PH_NEWTON);
 }
 
@@ -385,6 +414,15 @@ NDTB_HDF inline void ls_trial(OptState &s, const OptParams &prm) {
   opt_request(s, pose_mul(pose_from_vec(pincr), s.T), 0, PH_LS_EVAL);
 }
 
+NDTB_HDF inline void on_ls_init(OptState &s, const OptParams &prm, const double *sums7);
+NDTB_HDF inline void on_final(OptState &s, const OptParams &prm, double score);
+NDTB_HDF inline bool pose_same(const Pose &a, const Pose &b) {
+  bool eq = true;
+  for (int i = 0; i < 9; i++) eq = eq && (a.R[i] == b.R[i]);
+  for (int i = 0; i < 3; i++) eq = eq && (a.t[i] == b.t[i]);
+  return eq;
+}
+
 NDTB_HDF inline void opt_apply_step(OptState &s, const OptParams &prm, double step) {
   for (int i = 0; i < 6; i++) s.incr[i] *= step;
   s.T = pose_mul(pose_from_vec(s.incr), s.T);
@@ -397,24 +435,33 @@ NDTB_HDF inline void opt_apply_step(OptState &s, const OptParams &prm, double st
   s.itr++;
   if (!convergence)
     opt_request(s, s.T, 1, PH_NEWTON);
+  else if (s.have_last && pose_same(s.Plast, s.T))
+    on_final(s, prm, s.score_last);  // the final pose is the last trial pose: its score is already known
   else
     opt_request(s, s.T, 0, PH_FINAL);
 }
 
-NDTB_HDF inline void ls_start(OptState &s, int soft) {
+// lineSearchMT starts with a gradient-only derivativesNDT at the current pose (fusion.h:444 / :80): the Hessian pass of
+// this Newton iteration was evaluated at exactly that pose, so its score and gradient are handed over directly.
+NDTB_HDF inline void ls_start(OptState &s, const OptParams &prm, int soft) {
   s.ls_soft = soft;
   if (soft)
     for (int i = 0; i < 6; i++) s.X[i] = s.pose_local[i];
-  opt_request(s, s.T, 0, PH_LS_INIT);
+  on_ls_init(s, prm, s.sg);
+}
+
+NDTB_HDF inline void ls_finish_step(OptState &s, const OptParams &prm, double step) {
+  if (prm.fusion) step = step > 0.0 ? step : 0.0;  // fusion.h:1018-1023 with step_size_feat == 0
+  opt_apply_step(s, prm, step);
 }
 
 NDTB_HDF inline void ls_done(OptState &s, const OptParams &prm, double step) {
-  if (s.ls_soft) {  // fusion.h:1008-1023: the Tcov search result is overwritten by the NDT search
-    ls_start(s, 0);
+  if (s.ls_soft) {  // fusion.h:1008-1023: the Tcov search result is overwritten by the NDT search (same pose, same sums)
+    s.ls_soft = 0;
+    on_ls_init(s, prm, s.sg);
     return;
   }
-  if (prm.fusion) step = step > 0.0 ? step : 0.0;
-  opt_apply_step(s, prm, step);
+  ls_finish_step(s, prm, step);
 }
 
 // Resume with the reduced sums of the evaluation that was requested: sums[0]=score, [1..6]=g,
@@ -424,6 +471,9 @@ NDTB_HDF inline void opt_advance(OptState &s, const OptParams &prm, const double
   switch (s.phase) {
     case PH_NEWTON: {
       s.n_hess++;
+      s.n_exec++;
+      for (int i = 0; i < 7; i++) s.sg[i] = sums[i];
+      s.Plast = s.Peval, s.score_last = sums[0], s.have_last = 1;
       s.score_here = sums[0];
       double g[6], H[36];
       for (int i = 0; i < 6; i++) g[i] = sums[ACC_G + i];
@@ -498,45 +548,20 @@ NDTB_HDF inline void opt_advance(OptState &s, const OptParams &prm, const double
         return;
       }
       if (prm.step_control)
-        ls_start(s, prm.soft ? 1 : 0);
+        ls_start(s, prm, prm.soft ? 1 : 0);
       else
         opt_apply_step(s, prm, 1.0);
       return;
     }
-    case PH_LS_INIT: {
-      s.n_grad++;
-      double score_init = sums[0], gh[6];
-      for (int i = 0; i < 6; i++) gh[i] = sums[ACC_G + i];
-      if (s.ls_soft) {
-        score_init += maha_score(s.X, prm.Q);
-        double gm[6];
-        maha_gradient(s.X, prm.Q, gm);
-        for (int i = 0; i < 6; i++) gh[i] += gm[i];
-      }
-      s.dginit = 0;
-      for (int i = 0; i < 6; i++) s.dginit += s.incr[i] * gh[i];
-      if (s.dginit >= 0.0) {
-        for (int i = 0; i < 6; i++) s.incr[i] = -s.incr[i];
-        s.dginit = -s.dginit;
-        if (s.dginit >= 0.0) {
-          ls_done(s, prm, LS_RECOVERY);
-          return;
-        }
-      }
-      s.stp = 1.0;
-      s.infoc = 1;
-      s.brackt = 0, s.stage1 = 1, s.nfev = 0;
-      s.dgtest = LS_FTOL * s.dginit;
-      s.width = LS_STPMAX - LS_STPMIN;
-      s.width1 = 2 * s.width;
-      s.finit = score_init;
-      s.stx = 0.0, s.fx = s.finit, s.dgx = s.dginit;
-      s.sty = 0.0, s.fy = s.finit, s.dgy = s.dginit;
-      ls_trial(s, prm);
+    case PH_LS_INIT: {  // (not requested any more: ls_start answers it from the Hessian pass)
+      s.n_exec++;
+      on_ls_init(s, prm, sums);
       return;
     }
     case PH_LS_EVAL: {
       s.n_grad++;
+      s.n_exec++;
+      s.Plast = s.Peval, s.score_last = sums[0], s.have_last = 1;
       double f = sums[0], gh[6];
       for (int i = 0; i < 6; i++) gh[i] = sums[ACC_G + i];
       if (s.ls_soft) {
@@ -584,17 +609,61 @@ NDTB_HDF inline void opt_advance(OptState &s, const OptParams &prm, const double
       return;
     }
     case PH_FINAL: {
-      s.n_grad++;
-      s.score_here = sums[0];
-      if (prm.soft) s.score_here += maha_score(s.pose_local, prm.Q);
-      if (prm.tik) s.score_here += maha_score(s.x0, prm.Q);
-      if (s.score_here > s.score_best) s.T = s.Tbest;
-      opt_finish(s);
+      s.n_exec++;
+      on_final(s, prm, sums[0]);
       return;
     }
     default:
       return;
   }
+}
+
+NDTB_HDF inline void on_ls_init(OptState &s, const OptParams &prm, const double *sums7) {
+  for (;;) {
+    s.n_grad++;
+    double score_init = sums7[0], gh[6];
+    for (int i = 0; i < 6; i++) gh[i] = sums7[ACC_G + i];
+    if (s.ls_soft) {
+      score_init += maha_score(s.X, prm.Q);
+      double gm[6];
+      maha_gradient(s.X, prm.Q, gm);
+      for (int i = 0; i < 6; i++) gh[i] += gm[i];
+    }
+    s.dginit = 0;
+    for (int i = 0; i < 6; i++) s.dginit += s.incr[i] * gh[i];
+    if (s.dginit >= 0.0) {
+      for (int i = 0; i < 6; i++) s.incr[i] = -s.incr[i];
+      s.dginit = -s.dginit;
+      if (s.dginit >= 0.0) {  // no descent either way: the search returns the recovery step at once
+        if (s.ls_soft) {
+          s.ls_soft = 0;  // ... and the discarded Tcov search is followed by the NDT search
+          continue;
+        }
+        ls_finish_step(s, prm, LS_RECOVERY);
+        return;
+      }
+    }
+    s.stp = 1.0;
+    s.infoc = 1;
+    s.brackt = 0, s.stage1 = 1, s.nfev = 0;
+    s.dgtest = LS_FTOL * s.dginit;
+    s.width = LS_STPMAX - LS_STPMIN;
+    s.width1 = 2 * s.width;
+    s.finit = score_init;
+    s.stx = 0.0, s.fx = s.finit, s.dgx = s.dginit;
+    s.sty = 0.0, s.fy = s.finit, s.dgy = s.dginit;
+    ls_trial(s, prm);
+    return;
+  }
+}
+
+NDTB_HDF inline void on_final(OptState &s, const OptParams &prm, double score) {
+  s.n_grad++;
+  s.score_here = score;
+  if (prm.soft) s.score_here += maha_score(s.pose_local, prm.Q);
+  if (prm.tik) s.score_here += maha_score(s.x0, prm.Q);
+  if (s.score_here > s.score_best) s.T = s.Tbest;
+  opt_finish(s);
 }
 
 }  // namespace ndtb

@@ -21,7 +21,7 @@ typedef int (*hh_eval_cb)(const double *T16, int want_hess, double *sums28);
 struct hh_result {
   double T[16];
   double score, score_best;
-  int converged, iterations, n_hess, n_grad, exit_code, nonfinite;
+  int converged, iterations, n_hess, n_grad, exit_code, nonfinite, n_exec;
 };
 
 int hh_match(const double *T0, int itr_max, int step_control, int regularize, double delta_score, int fusion,
@@ -46,7 +46,7 @@ int hh_match(const double *T0, int itr_max, int step_control, int regularize, do
   pose_to_cm(s.T, out->T);
   out->score = s.score_here, out->score_best = s.score_best;
   out->converged = s.ret, out->iterations = s.itr, out->n_hess = s.n_hess, out->n_grad = s.n_grad;
-  out->exit_code = s.exit_code, out->nonfinite = s.nonfinite;
+  out->exit_code = s.exit_code, out->nonfinite = s.nonfinite, out->n_exec = s.n_exec;
   return 0;
 }
 

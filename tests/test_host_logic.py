@@ -1,0 +1,137 @@
+"""CPU suite, part 2: the engine's host/device-shared logic (csrc/d2d_pair.h closed-form pair contribution,
+csrc/optimizer.h resumable Newton / More-Thuente state machine) compiled for the HOST by tests/harness and checked
+against the oracle.  These are the exact sources nvcc compiles into the kernels."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def hh(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hh") / "libhh.so")
+    subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-fPIC", "-shared",
+                           "-ffp-contract=off", "-o", so, os.path.join(ROOT, "tests", "harness", "host_harness.cpp")])
+    return C.CDLL(so)
+
+
+class HResult(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("score", C.c_double), ("score_best", C.c_double), ("converged", C.c_int),
+                ("iterations", C.c_int), ("n_hess", C.c_int), ("n_grad", C.c_int), ("exit_code", C.c_int),
+                ("nonfinite", C.c_int), ("n_exec", C.c_int)]
+
+
+CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double))
+
+
+def _tri(S):
+    return np.array([S[0, 0], S[0, 1], S[0, 2], S[1, 1], S[1, 2], S[2, 2]])
+
+
+def test_pair_contribution_matches_oracle(hh, oracle):
+    rng = np.random.default_rng(0)
+
+    def rand_cov():
+        A = rng.normal(size=(3, 3)) * 0.1
+        return A @ A.T + 1e-3 * np.eye(3)
+
+    def one_cell_map(mean, cov):
+        cells = np.zeros(1, oracle.CELL_DTYPE)
+        cells["mean"], cells["cov"], cells["n"], cells["has_gaussian"] = mean, _tri(cov), 10, 1
+        return oracle.OracleMap(0.5).from_cells((0, 0, 0), (0.5,) * 3, (40, 40, 40), cells)
+
+    worst = 0.0
+    for _ in range(100):
+        m = rng.uniform(-5, 5, 3)
+        mu = m + rng.uniform(-0.6, 0.6, 3)
+        S, Cc = rand_cov(), rand_cov()
+        s, g, H, npairs = oracle.d2d_derivatives(one_cell_map(m, S), one_cell_map(mu, Cc), np.eye(4))
+        acc, g6 = np.zeros(28), np.zeros(6)
+        a = [np.ascontiguousarray(x) for x in (mu, _tri(Cc), m, _tri(S))]
+        ok = hh.hh_pair(*[x.ctypes.data_as(C.c_void_p) for x in a], C.c_double(1.0), C.c_double(0.05), 1,
+                        acc.ctypes.data_as(C.c_void_p), g6.ctypes.data_as(C.c_void_p))
+        assert ok == (1 if npairs else 0)
+        if not npairs:
+            continue
+        Hm = np.zeros((6, 6))
+        k = 7
+        for p in range(6):
+            for q in range(p, 6):
+                Hm[p, q] = Hm[q, p] = acc[k]
+                k += 1
+        worst = max(worst, abs(acc[0] - s), np.abs(acc[1:7] - g).max() / np.abs(g).max(), np.abs(Hm - H).max() / np.abs(H).max())
+        np.testing.assert_allclose(g6, acc[1:7], rtol=0, atol=0)
+    assert worst < 1e-12
+
+
+def _run_sm(hh, oracle, tm, sm, T0, p, fusion=0, Tcov=None):
+    evals = []
+
+    def cb(Tp, hess, sums):
+        T = np.array([Tp[i] for i in range(16)]).reshape(4, 4).T
+        s, g, H, _ = oracle.d2d_derivatives(tm, sm, T, p, bool(hess))
+        evals.append(hess)
+        sums[0] = s
+        for i in range(6):
+            sums[1 + i] = g[i]
+        k = 7
+        for a in range(6):
+            for b in range(a, 6):
+                sums[k] = H[a, b]
+                k += 1
+        return 0
+
+    r = HResult()
+    T0c = np.ascontiguousarray(np.asarray(T0).T).ravel().copy()
+    tc = np.ascontiguousarray(Tcov if Tcov is not None else np.eye(6))
+    rc = hh.hh_match(T0c.ctypes.data_as(C.c_void_p), p.itr_max, p.step_control, p.regularize, C.c_double(p.delta_score), fusion,
+                     p.use_soft_constraints, p.use_tikhonov, tc.ctypes.data_as(C.c_void_p), CB(cb), C.byref(r))
+    assert rc == 0
+    return r, evals
+
+
+@pytest.mark.parametrize("delta_score", [1e-3, 1e-6])
+def test_state_machine_reproduces_oracle_match(hh, oracle, golden, oracle_fixture_maps, delta_score):
+    p = oracle.default_params(delta_score=delta_score)
+    for k in range(7):
+        ro = oracle.d2d_match(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], golden[f"Todom{k}"], p)
+        r, evals = _run_sm(hh, oracle, oracle_fixture_maps[k], oracle_fixture_maps[k + 1], golden[f"Todom{k}"], p)
+        assert np.abs(np.array(r.T) - np.array(ro.T)).max() < 1e-12
+        assert (r.converged, r.iterations, r.n_hess, r.n_grad, r.exit_code) == (
+            ro.converged, ro.iterations, ro.n_hess_passes, ro.n_grad_passes, ro.exit_code)
+        # the evaluations the reference repeats at an already evaluated pose are not executed again
+        assert r.n_exec == len(evals) and r.n_exec <= r.n_hess + r.n_grad - r.iterations
+
+
+def test_state_machine_fusion_variants(hh, oracle, golden, oracle_fixture_maps):
+    Tcov = np.diag([0.01, 0.01, 1e-4, 1e-6, 1e-6, 0.001])
+    for soft, tik in ((1, 0), (0, 1), (1, 1)):
+        p = oracle.default_params(delta_score=1e-6, use_soft_constraints=soft, use_tikhonov=tik)
+        for k in (1, 2):
+            ro = oracle.fusion_match(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], golden[f"Todom{k}"], Tcov, p)
+            r, _ = _run_sm(hh, oracle, oracle_fixture_maps[k], oracle_fixture_maps[k + 1], golden[f"Todom{k}"], p, 1, Tcov)
+            assert np.abs(np.array(r.T) - np.array(ro.T)).max() < 1e-9
+            assert (r.converged, r.iterations, r.n_hess, r.n_grad, r.exit_code) == (
+                ro.converged, ro.iterations, ro.n_hess_passes, ro.n_grad_passes, ro.exit_code)
+
+
+def test_harness_linalg_matches_oracle(hh, oracle):
+    rng = np.random.default_rng(2)
+    for n in (3, 6):
+        for _ in range(20):
+            A = rng.normal(size=(n, n))
+            A = np.ascontiguousarray(A + A.T)
+            ev, V = np.zeros(n), np.zeros((n, n))
+            hh.hh_eig_sym(n, A.ctypes.data_as(C.c_void_p), ev.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+            eo, Vo = oracle.eig_sym(A)
+            assert np.array_equal(ev, eo) and np.array_equal(V, Vo)  # same algorithm, same operation order: bit-exact
+    for _ in range(20):
+        A = rng.normal(size=(6, 6))
+        A = np.ascontiguousarray(A @ A.T + 0.1 * np.eye(6))
+        b, x = rng.normal(size=6), np.zeros(6)
+        hh.hh_ldlt6(A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
+        np.testing.assert_allclose(A @ x, b, atol=1e-9)

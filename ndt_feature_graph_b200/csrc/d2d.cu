@@ -26,6 +26,9 @@ namespace ndtb {
 #ifndef NDTB_MATCH_THREADS
 #define NDTB_MATCH_THREADS 256
 #endif
+#ifndef NDTB_GRAD2
+#define NDTB_GRAD2 0  // gradient pass: two pairs per lane interleaved (measured slower on B200: spills)
+#endif
 #ifndef NDTB_PUSH_SCAN
 #define NDTB_PUSH_SCAN 1  // 1: one warp prefix scan per probe column; 0: one ballot per pushed hit
 #endif
@@ -101,6 +104,38 @@ __device__ __forceinline__ void process_entry(const PassCtx &c, const WarpScratc
 #pragma unroll
   for (int j = 0; j < 6; j++) S[j] = __ldg(t + 3 + j);
   if (pair_contrib<HESS>(mu0, mu1, mu2, C, m, S, c.lfd1, c.lfd2, acc, nullptr)) acc[ACC_PAIRS] += 1.0;
+}
+
+// gradient pass: two pairs per lane at once (independent dependency chains interleave, hiding the fp64 / exp / load
+// latencies that two resident warps per scheduler cannot hide)
+__device__ __forceinline__ void process_entry2(const PassCtx &c, const WarpScratch &ws, unsigned e0, unsigned e1, bool live1,
+                                               double *acc) {
+  const int sl0 = e0 >> 27, sl1 = e1 >> 27;
+  const double *t0 = c.tcell + (size_t)(e0 & 0x7FFFFFF) * GC, *t1 = c.tcell + (size_t)(e1 & 0x7FFFFFF) * GC;
+  double C0[6], m0[3], S0[6], C1[6], m1[3], S1[6];
+#pragma unroll
+  for (int j = 0; j < 3; j++) m0[j] = __ldg(t0 + j), m1[j] = __ldg(t1 + j);
+#pragma unroll
+  for (int j = 0; j < 6; j++) S0[j] = __ldg(t0 + 3 + j), S1[j] = __ldg(t1 + 3 + j);
+#pragma unroll
+  for (int j = 0; j < 6; j++) C0[j] = ws.stage[3 + j][sl0], C1[j] = ws.stage[3 + j][sl1];
+  pair_grad_nb(ws.stage[0][sl0], ws.stage[1][sl0], ws.stage[2][sl0], C0, m0, S0, c.lfd1, c.lfd2, true, acc, acc + ACC_PAIRS);
+  pair_grad_nb(ws.stage[0][sl1], ws.stage[1][sl1], ws.stage[2][sl1], C1, m1, S1, c.lfd1, c.lfd2, live1, acc, acc + ACC_PAIRS);
+}
+
+template <bool HESS>
+__device__ __forceinline__ void drain_batches(const PassCtx &c, WarpScratch &ws, int &qcount, int keep, int lane, double *acc) {
+  // process full batches of 32 pairs from the top of the queue until fewer than `keep` + 32 entries are left
+  if (!HESS && NDTB_GRAD2) {
+    while (qcount >= keep + 64) {
+      qcount -= 64;
+      process_entry2(c, ws, ws.queue[qcount + lane], ws.queue[qcount + 32 + lane], true, acc);
+    }
+  }
+  while (qcount >= keep + 32) {
+    qcount -= 32;
+    process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
+  }
 }
 
 // moved source cell: mean <- R mean + t (bit-exact operation order of the CPU restatement, the voxel of the
@@ -188,10 +223,7 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
         if (total == 0) continue;
         if (qcount + total > QCAP) {  // make room: drain the full batches
           __syncwarp();
-          while (qcount >= 32) {
-            qcount -= 32;
-            process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
-          }
+          drain_batches<HESS>(c, ws, qcount, 0, lane, acc);
           __syncwarp();
         }
         if (qcount + total <= QCAP) {
@@ -267,10 +299,7 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
     }
     // end of round: the staged cells are about to be overwritten — drain everything
     __syncwarp();
-    while (qcount >= 32) {
-      qcount -= 32;
-      process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
-    }
+    drain_batches<HESS>(c, ws, qcount, 0, lane, acc);
     if (qcount > 0) {
       if (lane < qcount) process_entry<HESS>(c, ws, ws.queue[lane], acc);
       qcount = 0;

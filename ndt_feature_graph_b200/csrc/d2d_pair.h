@@ -137,4 +137,45 @@ NDTB_HD bool pair_contrib(const double mu0, const double mu1, const double mu2, 
   return true;
 }
 
+// Branch-free gradient-only variant: a skipped pair contributes exact zeros through selects, so two calls on
+// independent pairs form one basic block and the scheduler interleaves their (long, serial) dependency chains.
+// Same operations in the same order as pair_contrib<false> for every pair that is not skipped.
+NDTB_HD void pair_grad_nb(const double mu0, const double mu1, const double mu2, const double *C /*6*/, const double *m /*3*/,
+                          const double *S /*6*/, double lfd1, double lfd2, bool live, double *acc, double *npairs) {
+  const double x0 = mu0 - m[0], x1 = mu1 - m[1], x2 = mu2 - m[2];
+  const double a00 = C[0] + S[0], a01 = C[1] + S[1], a02 = C[2] + S[2];
+  const double a11 = C[3] + S[3], a12 = C[4] + S[4], a22 = C[5] + S[5];
+  const double c00 = a11 * a22 - a12 * a12;
+  const double c10 = a02 * a12 - a01 * a22;
+  const double c20 = a01 * a12 - a02 * a11;
+  const double det = c00 * a00 + c10 * a01 + c20 * a02;
+  const bool ok1 = live && (fabs(det) > 1e-12);
+  const double id = 1.0 / (ok1 ? det : 1.0);
+  const double b00 = c00 * id, b01 = c10 * id, b02 = c20 * id;
+  const double b11 = (a00 * a22 - a02 * a02) * id;
+  const double b12 = (a02 * a01 - a00 * a12) * id;
+  const double b22 = (a00 * a11 - a01 * a01) * id;
+  const double q0 = b00 * x0 + b01 * x1 + b02 * x2;
+  const double q1 = b01 * x0 + b11 * x1 + b12 * x2;
+  const double q2 = b02 * x0 + b12 * x1 + b22 * x2;
+  const double l = x0 * q0 + x1 * q1 + x2 * q2;
+  const bool ok = ok1 && (l * 0.0 == 0.0);
+  const double sh = -lfd1 * exp(-lfd2 * (ok ? l : 0.0) * 0.5);
+  const double factor = -(lfd2 * 0.5) * sh;
+  acc[0] += ok ? sh : 0.0;
+  *npairs += ok ? 1.0 : 0.0;
+  const double w0 = C[0] * q0 + C[1] * q1 + C[2] * q2;
+  const double w1 = C[1] * q0 + C[3] * q1 + C[4] * q2;
+  const double w2 = C[2] * q0 + C[4] * q1 + C[5] * q2;
+  const double v0 = mu0 - w0, v1 = mu1 - w1, v2 = mu2 - w2;
+  const double Q0 = 2.0 * q0, Q1 = 2.0 * q1, Q2 = 2.0 * q2;
+  const double Q3 = 2.0 * (v1 * q2 - v2 * q1), Q4 = 2.0 * (v2 * q0 - v0 * q2), Q5 = 2.0 * (v0 * q1 - v1 * q0);
+  acc[ACC_G + 0] += ok ? factor * Q0 : 0.0;
+  acc[ACC_G + 1] += ok ? factor * Q1 : 0.0;
+  acc[ACC_G + 2] += ok ? factor * Q2 : 0.0;
+  acc[ACC_G + 3] += ok ? factor * Q3 : 0.0;
+  acc[ACC_G + 4] += ok ? factor * Q4 : 0.0;
+  acc[ACC_G + 5] += ok ? factor * Q5 : 0.0;
+}
+
 }  // namespace ndtb

@@ -31,41 +31,43 @@ __device__ __forceinline__ bool pt_skip(const float4 p, double range_limit) {
 
 // ---- guess-size grids: centroid in point order (one warp per map), then extents -------------------------
 // out[map*8 + {0,1,2}] = centroid sum / count, [3] = count, [4] = maxDist bits, [5] = max dz key, [6] = min dz key
-__global__ void k_centroid(const BuildJob *__restrict__ jobs, const int *__restrict__ which, double *__restrict__ out) {
+__global__ void __launch_bounds__(32) k_centroid(const BuildJob *__restrict__ jobs, const int *__restrict__ which, double *__restrict__ out) {
   const BuildJob &j = jobs[which[blockIdx.x]];
   const int lane = threadIdx.x;
-  double sx = 0, sy = 0, sz = 0;
+  // The sums are order dependent (every addition rounds), so they are taken in point order by ONE lane; the other
+  // lanes fetch (coalesced, two chunks ahead), filter and convert 32 points at a time into shared memory.
+  __shared__ double sx[2][32], sy[2][32], sz[2][32];
+  __shared__ unsigned smask[2];
+  double ax = 0, ay = 0, az = 0;
   long long cnt = 0;
-  // the sums must be taken in point order (each addition rounds): 32 points are fetched coalesced one chunk
-  // ahead, converted to double by their own lane, then broadcast one after the other
   float4 nxt = make_float4(0, 0, 0, 0);
   if (lane < j.npts) nxt = j.pts[lane];
-  for (int base = 0; base < j.npts; base += 32) {
+  int buf = 0;
+  for (int base = 0; base < j.npts; base += 32, buf ^= 1) {
     const float4 p = nxt;
     const int i = base + lane;
     if (i + 32 < j.npts) nxt = j.pts[i + 32];
     const bool use = i < j.npts && !pt_skip(p, j.range_limit);
-    const double dx = (double)p.x, dy = (double)p.y, dz = (double)p.z;
+    sx[buf][lane] = (double)p.x, sy[buf][lane] = (double)p.y, sz[buf][lane] = (double)p.z;
     const unsigned m = __ballot_sync(FULL, use);
-    if (m == FULL) {
+    if (lane == 0) smask[buf] = m;
+    __syncwarp();
+    if (lane == 0) {
+      if (m == FULL) {
 #pragma unroll
-      for (int r = 0; r < 32; r++) {
-        sx += __shfl_sync(FULL, dx, r);
-        sy += __shfl_sync(FULL, dy, r);
-        sz += __shfl_sync(FULL, dz, r);
-      }
-      cnt += 32;
-    } else {
-      for (int r = 0; r < 32; r++) {
-        const double x = __shfl_sync(FULL, dx, r), y = __shfl_sync(FULL, dy, r), z = __shfl_sync(FULL, dz, r);
-        if (m >> r & 1u) sx += x, sy += y, sz += z, cnt++;
+        for (int r = 0; r < 32; r++) ax += sx[buf][r], ay += sy[buf][r], az += sz[buf][r];
+        cnt += 32;
+      } else {
+        for (int r = 0; r < 32; r++)
+          if (m >> r & 1u) ax += sx[buf][r], ay += sy[buf][r], az += sz[buf][r], cnt++;
       }
     }
+    // double buffering: the next chunk is written to the other buffer while lane 0 may still be adding
   }
   if (lane == 0) {
     double *o = out + (size_t)blockIdx.x * 8;
     o[3] = (double)cnt;
-    if (cnt > 0) o[0] = sx / (double)cnt, o[1] = sy / (double)cnt, o[2] = sz / (double)cnt;
+    if (cnt > 0) o[0] = ax / (double)cnt, o[1] = ay / (double)cnt, o[2] = az / (double)cnt;
     unsigned long long *k = reinterpret_cast<unsigned long long *>(o);
     k[4] = 0ull;   // maxDist = +0.0
     k[5] = 0ull;   // ordered key of the smallest value
@@ -225,16 +227,66 @@ __device__ bool rescale_covariance(double *cov) {
 }
 
 // (a) one warp per touched block: record every cell's voxel key and sort its point ids ascending
-// (= insertion order of NDTCell::points_): shuffle ranking for n <= 32, bitonic network in shared memory up to
-// SORT_CAP, counting ranks beyond.
-constexpr int SORT_CAP = 1024;
+// (= insertion order of NDTCell::points_): shuffle ranking for n <= 32, a 64-element bitonic network in shared
+// memory up to 64, a stable warp radix sort beyond (cells next to the sensor hold thousands of points).
+constexpr int SORT_BITONIC_MAX = 64;
+
+// stable LSD radix sort (8-bit digits) of n point ids by one warp; ping-pongs between a and b, result in b
+__device__ void warp_radix_sort(int *a, int *b, int n, int bits, int *hist /*256, shared*/, int lane) {
+  const unsigned lt = (1u << lane) - 1u;
+  const int passes = (bits + 7) / 8;
+  int *in = a, *out = b;
+  if ((passes & 1) == 0) {  // even number of passes: start from b so that the last pass lands in b
+    for (int e = lane; e < n; e += 32) b[e] = a[e];
+    __syncwarp();
+    in = b, out = a;
+  }
+  for (int p = 0, shift = 0; p < passes; p++, shift += 8) {
+    for (int i = lane; i < 256; i += 32) hist[i] = 0;
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) atomicAdd(&hist[(in[e] >> shift) & 255], 1);
+    __syncwarp();
+    int local[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) local[q] = hist[lane * 8 + q], sum += local[q];
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, off);
+      if (lane >= off) incl += t;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int q = 0; q < 8; q++) hist[lane * 8 + q] = run, run += local[q];
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {  // chunks in order: stable
+      const int e = base + lane;
+      const bool act = e < n;
+      const int v = act ? in[e] : 0;
+      const int d = (v >> shift) & 255;
+      const unsigned am = __ballot_sync(FULL, act);
+      if (act) {
+        const unsigned peers = __match_any_sync(am, d);
+        const int leader = __ffs(peers) - 1;
+        int off = 0;
+        if (lane == leader) off = hist[d], hist[d] = off + __popc(peers);
+        off = __shfl_sync(peers, off, leader);
+        out[off + __popc(peers & lt)] = v;
+      }
+      __syncwarp();
+    }
+    int *t = in;
+    in = out, out = t;
+  }
+}
 
 __global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restrict__ jobs) {
-  __shared__ int sbuf[8][SORT_CAP];
+  __shared__ int sbuf[8][256];
   const BuildJob &j = jobs[blockIdx.y];
   const int lane = threadIdx.x & 31;
   int *sb = sbuf[threadIdx.x >> 5];
   const int ntb = j.counts[1];
+  const int bits = 32 - __clz(j.npts > 1 ? j.npts - 1 : 1);
   for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ntb; t += gridDim.x * 8) {
     const int b = j.tb_list[t];
     unsigned long long m = j.amask[b];
@@ -243,37 +295,27 @@ __global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restric
       if (lane == 0) j.cell_key[c] = b * 64 + (__ffsll((long long)m) - 1);
       const int n = j.cnt[c];
       if (n == 0) continue;
-      const int *seg = j.seg_idx + j.seg_off[c];
+      int *seg = j.seg_idx + j.seg_off[c];
       int *srt = j.seg2 + j.seg_off[c];
-      if (n <= 32) {
+      if (n <= 32) {  // ranks by 32 broadcasts
         const int v = lane < n ? seg[lane] : 0x7fffffff;
         int r = 0;
         for (int q = 0; q < n; q++) r += __shfl_sync(FULL, v, q) < v;
         if (lane < n) srt[r] = v;
-      } else if (n <= SORT_CAP) {
-        int mm = 64;
-        while (mm < n) mm <<= 1;
-        for (int e = lane; e < mm; e += 32) sb[e] = e < n ? seg[e] : 0x7fffffff;
+      } else if (n <= SORT_BITONIC_MAX) {  // 64-element bitonic network in shared memory
+        for (int e = lane; e < 64; e += 32) sb[e] = e < n ? seg[e] : 0x7fffffff;
         __syncwarp();
-        for (int k = 2; k <= mm; k <<= 1)
+        for (int k = 2; k <= 64; k <<= 1)
           for (int jj = k >> 1; jj > 0; jj >>= 1) {
-            for (int tt = lane; tt < (mm >> 1); tt += 32) {
-              const int i0 = 2 * tt - (tt & (jj - 1)), i1 = i0 + jj;
-              const int a0 = sb[i0], a1 = sb[i1];
-              const bool up = (i0 & k) == 0;
-              if ((a0 > a1) == up) sb[i0] = a1, sb[i1] = a0;
-            }
+            const int i0 = 2 * lane - (lane & (jj - 1)), i1 = i0 + jj;
+            const int a0 = sb[i0], a1 = sb[i1];
+            if ((a0 > a1) == ((i0 & k) == 0)) sb[i0] = a1, sb[i1] = a0;
             __syncwarp();
           }
         for (int e = lane; e < n; e += 32) srt[e] = sb[e];
         __syncwarp();
-      } else {
-        for (int e = lane; e < n; e += 32) {
-          const int v = seg[e];
-          int r = 0;
-          for (int q = 0; q < n; q++) r += seg[q] < v;
-          srt[r] = v;
-        }
+      } else {  // any size: stable radix sort through global memory (L1/L2 resident segments)
+        warp_radix_sort(seg, srt, n, bits, sb, lane);
       }
     }
   }

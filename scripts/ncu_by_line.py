@@ -9,7 +9,12 @@ from collections import defaultdict
 src_csv, sass, top = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40
 addr2line = {}
 cur = ("?", 0)
+nsec = 0
 for l in open(sass, errors="replace"):
+    if l.startswith(".text.") or l.lstrip().startswith(".section"):
+        nsec += 1
+        if nsec > 1 and addr2line:
+            break  # only the first function of the listing
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))

@@ -1,0 +1,92 @@
+"""The C++ host façade (include/ndtb_lslgeneric.hpp): the reference's class names over the C ABI.
+
+CPU: the façade test program compiles against the header + libndtb.so and fails loudly without a device.
+GPU: tests/harness/facade_corridor.cpp (the shape of ndt_feature/src/ndt_odom_debug.cpp:94-256 plus the graph entry
+point of ndt_feature_graph.cpp:347-353) runs on cuda:0 and every number it prints is compared with the oracle run on
+the clouds it dumped."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ndt_feature_graph_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+POSE_TOL = 1e-4  # north_star tolerance
+
+
+@pytest.fixture(scope="module")
+def facade_bin():
+    import __graft_entry__ as g
+
+    return g.build_facade_test()
+
+
+def test_facade_compiles_and_refuses_without_device(facade_bin):
+    out = subprocess.run([facade_bin, "--abi-check"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi ok" in out.stdout
+
+
+def _cm(v):
+    return np.array(v, dtype=np.float64).reshape(4, 4).T
+
+
+@pytest.mark.gpu
+def test_facade_corridor_matches_oracle(facade_bin, oracle, tmp_path):
+    out = subprocess.run([facade_bin, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    r = json.loads(out.stdout)
+    assert r["status"] == 0 and r["links_rc"] == 0
+    clouds = [np.fromfile(tmp_path / f, dtype=np.float32).reshape(-1, 4) for f in ("static.bin", "moving.bin", "third.bin")]
+    assert clouds[0].shape[0] == r["n_points"]
+    om = []
+    for c in clouds:
+        m = oracle.OracleMap(0.5)
+        m.set_map_size(80.0, 80.0, 2.0)
+        m.load_point_cloud(c, -1.0)
+        m.compute_cells()
+        om.append(m)
+    assert r["cells_static"] == om[0].num_cells(True) and r["cells_moving"] == om[1].num_cells(True)
+    assert r["n_pseudo"] == r["cells_static"]
+    odom, gt = _cm(r["odom"]), _cm(r["gt"])
+    # pseudoTransformNDT: first Gaussian cell (linear voxel order) moved by gt
+    c0 = om[0].export_cells(True)[0]
+    np.testing.assert_allclose(r["pseudo_mean0"], gt[:3, :3] @ c0["mean"] + gt[:3, 3], rtol=0, atol=1e-12)
+    # NDTMatcherD2D::match from the odometry guess
+    ro = oracle.d2d_match(om[0], om[1], odom)
+    Tg = _cm(r["T_d2d"])
+    assert synth.pose_error(ro.pose(), Tg) < POSE_TOL
+    assert (r["converged"], r["iterations"]) == (ro.converged, ro.iterations)
+    assert synth.pose_error(Tg, np.linalg.inv(gt)) < 0.05  # and it registers: moving = gt * static, so T -> gt^-1
+    # covariance and derivatives at the refined pose
+    rc, co = oracle.d2d_covariance(om[0], om[1], Tg)
+    assert rc == 0 and r["cov_ok"] == 1
+    np.testing.assert_allclose(np.array(r["cov"]).reshape(6, 6), co, rtol=1e-6, atol=1e-9 * np.abs(co).max())
+    so, go, Ho, _ = oracle.d2d_derivatives(om[0], om[1], Tg, want_hessian=True)
+    assert abs(r["score"] - so) <= 1e-10 * abs(so)
+    np.testing.assert_allclose(np.array(r["gradient"]), go, rtol=1e-8, atol=1e-9 * np.abs(go).max())
+    np.testing.assert_allclose(np.array(r["hessian"]).reshape(6, 6), Ho, rtol=1e-8, atol=1e-9 * np.abs(Ho).max())
+    # matchFusion with the soft constraint
+    Tcov = np.diag([0.01, 0.01, 1e-6, 1e-6, 1e-6, 0.001])
+    rf = oracle.fusion_match(om[0], om[1], odom, Tcov, oracle.default_params(delta_score=1e-6, use_soft_constraints=1))
+    assert synth.pose_error(rf.pose(), _cm(r["T_fusion"])) < POSE_TOL and r["fusion_ok"] == rf.converged
+    # graph edges: updateLinksUsingNDTRegistration
+    T0s = [odom, synth.pose2d(0.15, 0.0, 0.0), synth.pose2d(900.0, 900.0, 0.0)]
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    for i, ((a, b), T0) in enumerate(zip(pairs, T0s)):
+        rl = oracle.d2d_match(om[a], om[b], T0)
+        Tl = _cm(r[f"link{i}_T"])
+        assert synth.pose_error(rl.pose(), Tl) < POSE_TOL
+        assert r[f"link{i}_converged"] == rl.converged
+        cl = np.array(r[f"link{i}_cov"]).reshape(6, 6)
+        if rl.pose_changed:
+            _, col = oracle.d2d_covariance(om[a], om[b], rl.pose())
+            np.testing.assert_allclose(cl, col, rtol=1e-6, atol=1e-9 * np.abs(col).max())
+        else:
+            assert np.array_equal(cl, 0.02 * np.eye(6))  # ndt_feature_graph.cpp:300-310
+        so = oracle.overlap_occupancy_score(om[a], om[b], Tl)
+        assert abs(r[f"link{i}_score"] - so) <= 1e-12 * max(1.0, abs(so))
+    assert np.array_equal(_cm(r["link2_T"]), T0s[2])

@@ -169,7 +169,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     import ndt_feature_graph_b200 as N
-    from ndt_feature_graph_b200 import api, synth
+    from ndt_feature_graph_b200 import api, sharding, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +196,6 @@ def run_gpu(args):
     T0c = np.concatenate([np.ascontiguousarray(T.T).ravel() for T in T0s])
     d_res = torch.zeros(B * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d_cov = torch.zeros(B * 36, dtype=torch.float64, device=dev)
-    gather = torch.zeros(world * B * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev) if world > 1 else None
     in_bytes = 16 * (sum(c.shape[0] for c in tg) + sum(c.shape[0] for c in sr))
 
     def step_device():
@@ -204,7 +203,7 @@ def run_gpu(args):
                                d_res.data_ptr(), d_cov.data_ptr())
         if world > 1:  # the only cross-GPU step: gather of the per-edge result records (NCCL over NVLink)
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gather, d_res)
+                sharding.gather_results(d_res, world * B, rank, world)
 
     def sync_all():
         stream.synchronize()

@@ -45,6 +45,9 @@ struct ndtb_ctx {
   std::string last_error;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;  // event pairs around match-kernel launches
+  // host-buffer path: scans are uploaded on a second stream in chunks while the previous chunk's maps are being built
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
 };
 
 #define CU_TRY(ctx, expr)                                                                           \
@@ -619,6 +622,8 @@ int ndtb_ctx_create(int device, void *stream, ndtb_ctx **out) {
 void ndtb_ctx_destroy(ndtb_ctx *ctx) {
   if (!ctx) return;
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream), cudaStreamDestroy(ctx->copy_stream);
+  for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -788,19 +793,6 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
   if (!ctx || n_maps < 0 || (n_maps > 0 && (!maps || !pts || !n_pts))) return NDTB_ERR_ARG;
   std::vector<ndtb_map *> mv((size_t)n_maps);
   std::vector<PointSrc> ps((size_t)n_maps);
-  std::vector<SlabP> staged;
-  SlabP big;
-  if (mem != NDTB_MEM_DEVICE) {  // one slab, one H2D copy per scan
-    Carver c;
-    std::vector<size_t> off((size_t)n_maps);
-    for (int64_t i = 0; i < n_maps; i++) off[i] = c.take(16 * (size_t)n_pts[i]);
-    if (int rc = slab_alloc(ctx, c.off, big)) return rc;
-    for (int64_t i = 0; i < n_maps; i++) {
-      if (n_pts[i] > 0)
-        CU_TRY(ctx, cudaMemcpyAsync(big->p + off[i], pts[i], 16 * (size_t)n_pts[i], cudaMemcpyHostToDevice, ctx->stream));
-      ps[i] = {(const float4 *)(big->p + off[i]), (int)n_pts[i]};
-    }
-  }
   for (int64_t i = 0; i < n_maps; i++) {
     if (!maps[i] || n_pts[i] < 0 || n_pts[i] > 0x7fffffff) return NDTB_ERR_ARG;
     mv[i] = maps[i];
@@ -808,10 +800,64 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
     maps[i]->pending.clear();
     maps[i]->pending_load = false;
   }
-  std::vector<char> load((size_t)n_maps, 1);
-  std::vector<double> range((size_t)n_maps, range_limit);
   PhaseTimer pt(ctx, "map_build_batch");
-  const int rc = build_batch(ctx, mv, ps, load, range, maxnumpoints, occupancy_limit);
+  if (mem == NDTB_MEM_DEVICE) {
+    std::vector<char> load((size_t)n_maps, 1);
+    std::vector<double> range((size_t)n_maps, range_limit);
+    const int rc = build_batch(ctx, mv, ps, load, range, maxnumpoints, occupancy_limit);
+    pt.mark("build_batch");
+    return rc;
+  }
+  // Host scans: one slab; the H2D copies run on the copy stream in chunks of maps, chunk c+1 is in flight on PCIe
+  // while the kernels (and the host synchronisations) of chunk c's build run on the context's stream.
+  Carver c;
+  std::vector<size_t> off((size_t)n_maps);
+  size_t total = 0;
+  for (int64_t i = 0; i < n_maps; i++) off[i] = c.take(16 * (size_t)n_pts[i]), total += 16 * (size_t)n_pts[i];
+  SlabP big;
+  if (int rc = slab_alloc(ctx, c.off, big)) return rc;
+  for (int64_t i = 0; i < n_maps; i++) ps[i] = {(const float4 *)(big->p + off[i]), (int)n_pts[i]};
+  int n_chunks = 1;
+  if (n_maps >= 16 && total >= ((size_t)32 << 20)) n_chunks = (int)std::min<int64_t>(8, n_maps / 8);
+  if (n_chunks > 1 && !ctx->copy_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  while ((int)ctx->copy_events.size() < n_chunks + 1) {
+    cudaEvent_t e;
+    CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->copy_events.push_back(e);
+  }
+  cudaStream_t cs = n_chunks > 1 ? ctx->copy_stream : ctx->stream;
+  if (n_chunks > 1) {  // the slab is stream-ordered on ctx->stream: the copy stream may touch it only after its allocation
+    CU_TRY(ctx, cudaEventRecord(ctx->copy_events[n_chunks], ctx->stream));
+    CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->copy_events[n_chunks], 0));
+  }
+  std::vector<int64_t> cbeg((size_t)n_chunks + 1, 0);
+  {  // chunk boundaries at (roughly) equal bytes
+    size_t acc = 0;
+    int cc = 1;
+    for (int64_t i = 0; i < n_maps && cc < n_chunks; i++) {
+      acc += 16 * (size_t)n_pts[i];
+      if (acc * n_chunks >= total * cc) cbeg[cc++] = i + 1;
+    }
+    for (; cc <= n_chunks; cc++) cbeg[cc] = n_maps;
+  }
+  for (int k = 0; k < n_chunks; k++) {
+    for (int64_t i = cbeg[k]; i < cbeg[k + 1]; i++)
+      if (n_pts[i] > 0) CU_TRY(ctx, cudaMemcpyAsync(big->p + off[i], pts[i], 16 * (size_t)n_pts[i], cudaMemcpyHostToDevice, cs));
+    if (n_chunks > 1) CU_TRY(ctx, cudaEventRecord(ctx->copy_events[k], cs));
+  }
+  pt.mark("enqueue H2D");
+  int rc = NDTB_OK;
+  for (int k = 0; k < n_chunks && rc == NDTB_OK; k++) {
+    const int64_t b = cbeg[k], e = cbeg[k + 1];
+    if (e <= b) continue;
+    if (n_chunks > 1) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[k], 0));
+    std::vector<ndtb_map *> cm(mv.begin() + b, mv.begin() + e);
+    std::vector<PointSrc> cp(ps.begin() + b, ps.begin() + e);
+    std::vector<char> load((size_t)(e - b), 1);
+    std::vector<double> range((size_t)(e - b), range_limit);
+    rc = build_batch(ctx, cm, cp, load, range, maxnumpoints, occupancy_limit);
+  }
+  if (rc != NDTB_OK && n_chunks > 1) cudaStreamSynchronize(cs);  // the slab must outlive the copies in flight
   pt.mark("build_batch");
   return rc;
 }

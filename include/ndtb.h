@@ -19,6 +19,7 @@
  *                        (the serial loop over links becomes one batched launch)
  *   ndtb_register_scans  NDTFeatureFuserHMT::update front-end step, ndt_feature_fuser_hmt.cpp:195-227
  *                        (local map of the scan) + :356-357 (match) + :399-420 (covariance), batched
+ *   ndtb_p2d_match       NDTMatcherP2D::match [upstream]; no call site in the reference (BASELINE.json config C3)
  *   ndtb_overlap_score   NDTFeatureNode::overlapNDTOccupancyScore, ndt_feature/include/ndt_feature/ndt_feature_node.h:213-252
  *
  * Conventions
@@ -184,6 +185,15 @@ int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src,
 int ndtb_d2d_match_batch(ndtb_ctx *ctx, int64_t n_edges, const ndtb_map *const *tgt,
                          const ndtb_map *const *src, const double *T0s, const ndtb_params *p,
                          int with_covariance, int out_mem, ndtb_result *res, double *cov36s);
+
+/* ---- NDTMatcherP2D [upstream; no call site in the reference — BASELINE config C3] ----------------- */
+/* Point-to-distribution NDT of a cloud (n x 4 float, host or device memory) against a map: the D2D score /
+ * gradient / Hessian with a zero source covariance, the neighbourhood and the Newton / More-Thuente driver of
+ * NDTMatcherD2D (DESIGN.md "P2D"; parity unpinned, defined by the oracle). */
+int ndtb_p2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const float *pts, int64_t n, int mem, const double *T,
+                         const ndtb_params *p, int want_hessian, double *out43, int64_t *n_pairs);
+int ndtb_p2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const float *pts, int64_t n, int mem, const double *T0,
+                   const ndtb_params *p, ndtb_result *res);
 
 /* Batched front-end step: for each pair build the NDT map of the target scan and of the source scan
  * (cell size `cell`, guess-size grids unless map_size[0..2] > 0: then setMapSize), register source onto

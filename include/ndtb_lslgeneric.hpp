@@ -13,6 +13,7 @@
 //   lslgeneric::NDTCell {getMean,getCov,setMean,setCov,getCenter,getOccupancy,hasGaussian_}
 //   lslgeneric::NDTMatcherD2D {n_neighbours, ITR_MAX, DELTA_SCORE, step_control; match; covariance; derivativesNDT}
 //                                                                         ndt_feature_graph.cpp:261-298, ndt_matcher_d2d_fusion.h:856
+//   lslgeneric::NDTMatcherP2D {match}                                      (no call site in the reference; BASELINE config C3)
 //   ndt_feature::matchFusion (NDT term + soft constraint / Tikhonov)       ndt_matcher_d2d_fusion.h:797-1155
 //   ndt_feature::overlapNDTOccupancyScore                                  ndt_feature_node.h:213-252
 //   ndtb::GraphRegistrar::updateLinksUsingNDTRegistration                  ndt_feature_graph.cpp:347-353 (one batched launch)
@@ -432,6 +433,36 @@ class NDTMatcherD2D {
     return out[0];
   }
   ndtb_result last = {};
+};
+
+// NDTMatcherP2D [upstream]: point cloud against an NDT map.  Not referenced by ndt_feature_graph itself (BASELINE
+// config C3 names it); same knobs as NDTMatcherD2D.
+class NDTMatcherP2D {
+ public:
+  int n_neighbours = 2;
+  int ITR_MAX = 30;
+  double DELTA_SCORE = 10e-3 * 0.1;
+  bool step_control = true;
+  ndtb_result last = {};
+
+  // match(target map, source cloud, T, useInitialGuess) -> converged; T refined in place
+  template <class Cloud, class Affine>
+  bool match(NDTMap &target, const Cloud &source, Affine &T, bool useInitialGuess = false) {
+    ndtb_ctx *c = ndtb::context();
+    if (!c || !target.handle()) return false;
+    double T0[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (useInitialGuess) std::memcpy(T0, ndtb::pose_data(T), sizeof T0);
+    ndtb_params p;
+    ndtb_default_params(&p);
+    p.n_neighbours = n_neighbours, p.itr_max = ITR_MAX, p.delta_score = DELTA_SCORE, p.step_control = step_control;
+    ndtb_result r;
+    ndtb::last_status() = ndtb_p2d_match(c, target.handle(), reinterpret_cast<const float *>(source.points.data()),
+                                         (int64_t)source.points.size(), NDTB_MEM_HOST, T0, &p, &r);
+    if (ndtb::last_status() != NDTB_OK) return false;
+    std::memcpy(ndtb::pose_data(T), r.T, sizeof r.T);
+    last = r;
+    return r.converged != 0;
+  }
 };
 
 }  // namespace lslgeneric

@@ -130,6 +130,8 @@ def load_library():
         "ndtb_d2d_match": (C.c_int, [vp, vp, vp, vp, PP, PR]),
         "ndtb_fusion_match": (C.c_int, [vp, vp, vp, vp, vp, PP, PR]),
         "ndtb_d2d_covariance": (C.c_int, [vp, vp, vp, vp, PP, vp]),
+        "ndtb_p2d_derivatives": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, PP, C.c_int, vp, C.POINTER(i64)]),
+        "ndtb_p2d_match": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, PP, PR]),
         "ndtb_d2d_match_batch": (C.c_int, [vp, i64, vp, vp, vp, PP, C.c_int, C.c_int, vp, vp]),
         "ndtb_register_scans": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, dbl, vp, dbl, PP, C.c_int, C.c_int, C.c_int, vp, vp]),
         "ndtb_overlap_score": (C.c_int, [vp, vp, vp, vp, C.POINTER(dbl)]),
@@ -405,3 +407,29 @@ class NDTMatcherD2D:
         if rc not in (0, -5):
             self.e.check(rc)
         return rc == 0, out.reshape(6, 6)
+
+
+class NDTMatcherP2D:
+    """lslgeneric::NDTMatcherP2D (no call site in the reference; BASELINE config C3): point cloud against an NDT map."""
+
+    def __init__(self, engine, **knobs):
+        self.e = engine
+        self.params = engine.default_params(**knobs)
+
+    def derivativesPointCloud(self, target, cloud, T, computeHessian=True):
+        pts = _pts4(cloud)
+        out = np.zeros(43)
+        Tc = _cm(T)
+        npairs = C.c_int64(0)
+        self.e.check(self.e.L.ndtb_p2d_derivatives(self.e.h, target.h, pts.ctypes.data, pts.shape[0], HOST, Tc.ctypes.data,
+                                                   C.byref(self.params), int(computeHessian), out.ctypes.data, C.byref(npairs)))
+        return out[0], out[1:7].copy(), out[7:].reshape(6, 6).copy(), npairs.value
+
+    def match(self, target, cloud, T, useInitialGuess=True):
+        pts = _pts4(cloud)
+        T0 = np.asarray(T, dtype=np.float64) if useInitialGuess else np.eye(4)
+        r = Result()
+        Tc = _cm(T0)
+        self.e.check(self.e.L.ndtb_p2d_match(self.e.h, target.h, pts.ctypes.data, pts.shape[0], HOST, Tc.ctypes.data,
+                                             C.byref(self.params), C.byref(r)))
+        return r

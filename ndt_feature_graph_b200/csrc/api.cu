@@ -1075,6 +1075,49 @@ int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src,
   return status;
 }
 
+// ---- NDTMatcherP2D: the cloud becomes a list of zero-covariance cells that the D2D kernels consume
+namespace {
+int points_source(ndtb_ctx *ctx, const float *pts, int64_t n, int mem, std::unique_ptr<ndtb_map> &out) {
+  if (n < 0 || n > 0x7fffffff || (n > 0 && !pts)) return NDTB_ERR_ARG;
+  SlabP pbuf, cbuf;
+  const float4 *d_pts = (const float4 *)pts;
+  if (mem != NDTB_MEM_DEVICE) {
+    if (int rc = stage_points(ctx, pts, n, mem, pbuf)) return rc;
+    d_pts = (const float4 *)pbuf->p;
+  }
+  if (int rc = slab_alloc(ctx, 256 + 8 * (size_t)GC * (size_t)std::max<int64_t>(n, 1), cbuf)) return rc;
+  CU_TRY(ctx, cudaMemsetAsync(cbuf->p, 0xFF, 256, ctx->stream));  // a 2-entry empty block table (never probed: sources have no table)
+  if (n > 0) ctx->launches += launch_points_as_cells(d_pts, (int)n, (double *)(cbuf->p + 256), ctx->stream);
+  out.reset(new ndtb_map());
+  ndtb_map *m = out.get();
+  m->ctx = ctx;
+  m->cell[0] = m->cell[1] = m->cell[2] = 1.0;
+  std::memset(&m->g, 0, sizeof m->g);
+  m->grid_ready = true;
+  m->s_cells = cbuf;
+  m->table = (HashEntry *)cbuf->p, m->tsize = 2;
+  m->gcell = (double *)(cbuf->p + 256), m->ng = (int)n;
+  return NDTB_OK;
+}
+}  // namespace
+
+int ndtb_p2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const float *pts, int64_t n, int mem, const double *T,
+                         const ndtb_params *p, int want_hessian, double *out43, int64_t *n_pairs) {
+  if (!ctx || !tgt || !T || !p || !out43) return NDTB_ERR_ARG;
+  std::unique_ptr<ndtb_map> src;
+  if (int rc = points_source(ctx, pts, n, mem, src)) return rc;
+  return ndtb_d2d_derivatives(ctx, tgt, src.get(), T, p, want_hessian, out43, n_pairs);
+}
+
+int ndtb_p2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const float *pts, int64_t n, int mem, const double *T0,
+                   const ndtb_params *p, ndtb_result *res) {
+  if (!ctx || !tgt || !T0 || !p || !res) return NDTB_ERR_ARG;
+  std::unique_ptr<ndtb_map> src;
+  if (int rc = points_source(ctx, pts, n, mem, src)) return rc;
+  const ndtb_map *sp = src.get();
+  return match_batch_impl(ctx, 1, &tgt, &sp, T0, nullptr, p, 0, NDTB_MEM_HOST, res, nullptr);
+}
+
 int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_pts, const int64_t *n_tgt,
                         const float *const *src_pts, const int64_t *n_src, const double *T0s, double cell,
                         const double *map_size, double range_limit, const ndtb_params *p, int with_covariance, int in_mem,

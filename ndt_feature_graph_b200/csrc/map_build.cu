@@ -526,6 +526,18 @@ __global__ void k_point_indices(GridDesc g, const float4 *__restrict__ pts, int 
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_in, local);
 }
 
+// NDTMatcherP2D: a point is handed to the D2D kernels as a cell with mean p and zero covariance (DESIGN.md "P2D").
+// NaN points keep a NaN mean: the matcher's voxel lookup rejects them, like the CPU restatement which drops them.
+__global__ void k_points_as_cells(const float4 *__restrict__ pts, int n, double *__restrict__ gcell) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    double *o = gcell + (size_t)i * GC;
+    o[0] = (double)p.x, o[1] = (double)p.y, o[2] = (double)p.z;
+#pragma unroll
+    for (int q = 3; q < GC; q++) o[q] = 0.0;
+  }
+}
+
 // ndt_feature::overlapNDTOccupancyScore (ndt_feature/include/ndt_feature/ndt_feature_node.h:213-252):
 // mean squared difference of rescaled occupancies over the initialised cells of `mov` mapped into `ref`.
 // Integer-free sums are accumulated per cell in (block, bit) order by ONE thread block with a fixed tree.
@@ -624,6 +636,10 @@ int launch_from_cells_place(const BuildJob *d_job, const ndtb_cell *d_cells, int
 }
 int launch_point_indices(const GridDesc &g, const float4 *d_pts, int n, int *d_out, int *d_nin, cudaStream_t s) {
   k_point_indices<<<chunks_for(n, 1024), 256, 0, s>>>(g, d_pts, n, d_out, d_nin);
+  return 1;
+}
+int launch_points_as_cells(const float4 *d_pts, int n, double *d_gcell, cudaStream_t s) {
+  k_points_as_cells<<<chunks_for(n, 1024), 256, 0, s>>>(d_pts, n, d_gcell);
   return 1;
 }
 int launch_overlap(const BuildJob *d_jobs2, const double *d_T16, double *d_out, cudaStream_t s) {

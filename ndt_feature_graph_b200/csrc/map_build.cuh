@@ -58,6 +58,7 @@ int launch_from_cells_voxel(const BuildJob *d_job, const ndtb_cell *d_cells, int
                             cudaStream_t s);
 int launch_from_cells_place(const BuildJob *d_job, const ndtb_cell *d_cells, int n, const int *d_vox, cudaStream_t s);
 int launch_point_indices(const GridDesc &g, const float4 *d_pts, int n, int *d_out, int *d_nin, cudaStream_t s);
+int launch_points_as_cells(const float4 *d_pts, int n, double *d_gcell, cudaStream_t s);
 int launch_overlap(const BuildJob *d_jobs2, const double *d_T16, double *d_out, cudaStream_t s);
 
 }  // namespace ndtb

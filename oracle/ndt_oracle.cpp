@@ -890,10 +890,36 @@ struct Fusion {
   const double *Tcov;  // 6x6 row-major
 };
 
+int match_cells(const orc_map &tgt, const std::vector<Gauss> &src, const double *T0, const orc_params &prm,
+                const Fusion *fusion, orc_result &res);
+
 int match_impl(const orc_map &tgt, const orc_map &srcmap, const double *T0, const orc_params &prm, const Fusion *fusion,
                orc_result &res) {
   std::vector<Gauss> src;
   srcmap.gaussians(src);
+  return match_cells(tgt, src, T0, prm, fusion, res);
+}
+
+// NDTMatcherP2D [upstream, no call site in the reference: parity unpinned, defined here].  Point-to-distribution NDT
+// (Magnusson): score = sum_points sum_{cells in the (2k+1)^3 neighbourhood} -lfd1 exp(-lfd2/2 x^T S^-1 x), x = T p - m.
+// Its gradient / Hessian are exactly the D2D expressions with a zero source covariance (every Z term vanishes), so a
+// point is handed to the D2D machinery as a cell with mean p and covariance 0; the Newton / More-Thuente driver is the
+// one of NDTMatcherD2D::match.
+void points_as_cells(const float *pts, int64_t n, std::vector<Gauss> &out) {
+  out.clear();
+  out.reserve((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    const float *p = pts + 4 * i;
+    if (std::isnan(p[0]) || std::isnan(p[1]) || std::isnan(p[2])) continue;
+    Gauss g;
+    g.mean[0] = p[0], g.mean[1] = p[1], g.mean[2] = p[2];
+    for (int k = 0; k < 9; k++) g.cov[k] = 0.0;
+    out.push_back(g);
+  }
+}
+
+int match_cells(const orc_map &tgt, const std::vector<Gauss> &src, const double *T0, const orc_params &prm,
+                const Fusion *fusion, orc_result &res) {
   Pose T = pose_from_cm(T0), Tbest = T;
   const Pose Tinit = T;
   double score_best = fusion ? std::numeric_limits<double>::max() : (double)2147483647;  // INT_MAX upstream
@@ -1296,6 +1322,25 @@ int orc_fusion_match(const orc_map *tgt, const orc_map *src, const double *T0, c
                      const orc_params *p, orc_result *res) {
   Fusion f{Tcov36};
   return match_impl(*tgt, *src, T0, *p, &f, *res);
+}
+
+int orc_p2d_derivatives(const orc_map *tgt, const float *pts, int64_t n, const double *T, const orc_params *p,
+                        int want_hessian, double *out43, int64_t *n_pairs) {
+  std::vector<Gauss> s;
+  points_as_cells(pts, n, s);
+  Deriv D;
+  derivatives_cells(s, pose_from_cm(T), *tgt, *p, want_hessian != 0, D);
+  out43[0] = D.score;
+  for (int i = 0; i < 6; i++) out43[1 + i] = D.g[i];
+  for (int i = 0; i < 36; i++) out43[7 + i] = want_hessian ? D.H[i] : 0.0;
+  if (n_pairs) *n_pairs = D.pairs;
+  return 0;
+}
+
+int orc_p2d_match(const orc_map *tgt, const float *pts, int64_t n, const double *T0, const orc_params *p, orc_result *res) {
+  std::vector<Gauss> s;
+  points_as_cells(pts, n, s);
+  return match_cells(*tgt, s, T0, *p, nullptr, *res);
 }
 
 int orc_d2d_covariance(const orc_map *tgt, const orc_map *src, const double *T, const orc_params *p, double *cov36) {

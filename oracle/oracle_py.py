@@ -95,6 +95,8 @@ def lib():
     L.orc_map_point_indices.argtypes = [vp, vp, i64, vp]
     L.orc_d2d_derivatives.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_int, vp, C.POINTER(i64)]
     L.orc_d2d_match.argtypes = [vp, vp, vp, C.POINTER(Params), C.POINTER(Result)]
+    L.orc_p2d_derivatives.argtypes = [vp, vp, i64, vp, C.POINTER(Params), C.c_int, vp, C.POINTER(i64)]
+    L.orc_p2d_match.argtypes = [vp, vp, i64, vp, C.POINTER(Params), C.POINTER(Result)]
     L.orc_fusion_match.argtypes = [vp, vp, vp, vp, C.POINTER(Params), C.POINTER(Result)]
     L.orc_d2d_covariance.argtypes = [vp, vp, vp, C.POINTER(Params), vp]
     L.orc_d2d_match_batch.argtypes = [i64, vp, vp, vp, C.POINTER(Params), C.c_int, C.c_int, vp, vp]
@@ -205,6 +207,28 @@ def d2d_match(tgt, src, T0, params=None):
     r = Result()
     Tc = _cm(T0)
     rc = lib().orc_d2d_match(tgt.h, src.h, Tc.ctypes.data, C.byref(p), C.byref(r))
+    assert rc == 0
+    return r
+
+
+def p2d_derivatives(tgt, pts, T, params=None, want_hessian=True):
+    """NDTMatcherP2D derivatives of the cloud `pts` moved by T against the map (D2D with zero source covariance)."""
+    p = params or default_params()
+    pts = _pts4(pts)
+    out = np.zeros(43)
+    Tc = _cm(T)
+    npairs = C.c_int64(0)
+    lib().orc_p2d_derivatives(tgt.h, pts.ctypes.data, pts.shape[0], Tc.ctypes.data, C.byref(p), int(want_hessian),
+                              out.ctypes.data, C.byref(npairs))
+    return out[0], out[1:7].copy(), out[7:].reshape(6, 6).copy(), npairs.value
+
+
+def p2d_match(tgt, pts, T0, params=None):
+    p = params or default_params()
+    pts = _pts4(pts)
+    r = Result()
+    Tc = _cm(T0)
+    rc = lib().orc_p2d_match(tgt.h, pts.ctypes.data, pts.shape[0], Tc.ctypes.data, C.byref(p), C.byref(r))
     assert rc == 0
     return r
 

@@ -168,6 +168,10 @@ int main(int argc, char **argv) {
   Eigen::Affine3d T_fusion = odom_transform;
   const bool fusion_ok = ndt_feature::matchFusion(ndt, mov, T_fusion, Tcov, true, true, 30, n_neighbours, 1e-6, true, false);
 
+  lslgeneric::NDTMatcherP2D p2d;
+  Eigen::Affine3d T_p2d = odom_transform;
+  const bool p2d_ok = p2d.match(ndt, moving_pc, T_p2d, true);
+
   // graph edge refinement over three nodes (ndt_feature_graph.cpp:347-353)
   std::vector<NDTMap *> nodes = {&ndt, &mov, &third};
   ndtb::GraphRegistrar graph(nodes);
@@ -198,6 +202,8 @@ int main(int argc, char **argv) {
   print_mat("cov", cov);
   print_mat("gradient", g);
   print_mat("hessian", H);
+  print_pose("T_p2d", T_p2d);
+  std::printf("\"p2d_ok\": %d, \"p2d_iterations\": %d,\n", (int)p2d_ok, p2d.last.iterations);
   print_pose("T_fusion", T_fusion);
   std::printf("\"fusion_ok\": %d, \"links_rc\": %d,\n", (int)fusion_ok, rc);
   for (int i = 0; i < 3; i++) {

@@ -73,6 +73,10 @@ def test_facade_corridor_matches_oracle(facade_bin, oracle, tmp_path):
     Tcov = np.diag([0.01, 0.01, 1e-6, 1e-6, 1e-6, 0.001])
     rf = oracle.fusion_match(om[0], om[1], odom, Tcov, oracle.default_params(delta_score=1e-6, use_soft_constraints=1))
     assert synth.pose_error(rf.pose(), _cm(r["T_fusion"])) < POSE_TOL and r["fusion_ok"] == rf.converged
+    # NDTMatcherP2D: the moving cloud against the static map
+    rp = oracle.p2d_match(om[0], clouds[1], odom)
+    assert synth.pose_error(rp.pose(), _cm(r["T_p2d"])) < POSE_TOL
+    assert (r["p2d_ok"], r["p2d_iterations"]) == (rp.converged, rp.iterations)
     # graph edges: updateLinksUsingNDTRegistration
     T0s = [odom, synth.pose2d(0.15, 0.0, 0.0), synth.pose2d(900.0, 900.0, 0.0)]
     pairs = [(0, 1), (0, 2), (1, 2)]

@@ -314,3 +314,39 @@ def test_determinism(engine, c2small):
     a = m.match(gm[0], gm[1], T0)
     b = m.match(gm[0], gm[1], T0)
     assert list(a.T) == list(b.T) and a.score == b.score
+
+
+# ------------------------------------------------------------------ NDTMatcherP2D (config C3; no call site in the reference)
+def test_p2d_derivatives_and_match(oracle, engine, c1, c2small):
+    import ndt_feature_graph_b200 as N
+
+    m = N.NDTMatcherP2D(engine)
+    for (ca, cb, D, om, gm), planar in ((c1, True), (c2small, False)):
+        for T in (D, synth.perturb_pose(D, 3, dt=0.05, dr=0.01, planar=planar)):
+            so, go, Ho, no = oracle.p2d_derivatives(om[0], cb, T)
+            sg, gg, Hg, ng = m.derivativesPointCloud(gm[0], cb, T)
+            assert no == ng and no > 0
+            assert _rel(sg, so) < 1e-10 and _rel(gg, go) < 1e-9 and _rel(Hg, Ho) < 1e-9
+        n_stable = 0
+        for seed in range(4):
+            T0 = synth.perturb_pose(D, 20 + seed, dt=0.1, dr=0.02, planar=planar)
+            ro = oracle.p2d_match(om[0], cb, T0)
+            r3 = oracle.p2d_match(om[0], cb, T0, oracle.default_params(n_threads=3))
+            rg = m.match(gm[0], cb, T0)
+            if synth.pose_error(ro.pose(), r3.pose()) > 1e-9:
+                continue  # the oracle does not reproduce itself under another summation order (chaotic start)
+            n_stable += 1
+            assert synth.pose_error(ro.pose(), rg.pose()) < 1e-4  # north-star tolerance
+            assert (ro.converged, ro.iterations) == (rg.converged, rg.iterations)
+            if planar:
+                assert synth.pose_error(rg.pose(), D) < 0.01  # dense 2-D walls: P2D registers
+        assert n_stable >= 2
+    # NaN points are skipped, an empty cloud leaves the pose unchanged
+    ca, cb, D, om, gm = c1
+    bad = cb.copy()
+    bad[::7, 1] = np.nan
+    so, go, _, no = oracle.p2d_derivatives(om[0], bad, D, want_hessian=False)
+    sg, gg, _, ng = m.derivativesPointCloud(gm[0], bad, D, computeHessian=False)
+    assert no == ng and _rel(sg, so) < 1e-10 and _rel(gg, go) < 1e-9
+    r = m.match(gm[0], np.zeros((0, 4), np.float32), D)
+    assert r.pose_changed == 0

@@ -136,3 +136,31 @@ def test_robust_yaw_cases(oracle):
     for yaw in (-3.1, -1.5, -0.3, 0.0, 0.4, 2.9):
         T = synth.pose2d(1.0, -2.0, yaw)
         assert abs(oracle.robust_yaw(T) - yaw) < 1e-12
+
+
+def test_oracle_p2d_finite_differences_and_known_answer(oracle):
+    """NDTMatcherP2D restatement (no call site in the reference, parity unpinned): its gradient / Hessian are checked by
+    central differences of the scalar score, and on a dense 2-D room it registers to the ground truth."""
+    from ndt_feature_graph_b200 import synth
+
+    ca, cb, D = synth.laser2d_pair(1, n_rays=3000)
+    m = oracle.OracleMap(0.5)
+    m.load_point_cloud(ca, -1.0)
+    m.compute_cells()
+    T = synth.perturb_pose(D, 2, dt=0.05, dr=0.01, planar=True)
+    s0, g, H, npairs = oracle.p2d_derivatives(m, cb, T)
+    assert npairs > 1000
+    eps = 1e-6
+    gn, Hn = np.zeros(6), np.zeros((6, 6))
+    for i in range(6):
+        d = np.zeros(6)
+        d[i] = eps
+        sp, gp, _, _ = oracle.p2d_derivatives(m, cb, oracle.pose_from_vec(d) @ T, want_hessian=False)
+        sm, gm_, _, _ = oracle.p2d_derivatives(m, cb, oracle.pose_from_vec(-d) @ T, want_hessian=False)
+        gn[i] = (sp - sm) / (2 * eps)
+        Hn[:, i] = (gp - gm_) / (2 * eps)
+    assert np.abs(gn - g).max() <= 1e-6 * np.abs(g).max()
+    # the increment is applied on the left (T <- TR(p) T), so gradients at p != 0 differ from the p = 0 Hessian only at O(eps)
+    assert np.abs(Hn - H).max() <= 2e-4 * np.abs(H).max()
+    r = oracle.p2d_match(m, cb, synth.perturb_pose(D, 5, dt=0.1, dr=0.02, planar=True))
+    assert r.converged and synth.pose_error(r.pose(), D) < 0.01

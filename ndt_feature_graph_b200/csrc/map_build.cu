@@ -31,43 +31,92 @@ __device__ __forceinline__ bool pt_skip(const float4 p, double range_limit) {
 
 // ---- guess-size grids: centroid in point order (one warp per map), then extents -------------------------
 // out[map*8 + {0,1,2}] = centroid sum / count, [3] = count, [4] = maxDist bits, [5] = max dz key, [6] = min dz key
+//
+// The reference adds the coordinates one by one in point order (every addition rounds), so the sum is order dependent.
+// It is reproduced bit for bit without walking the points one at a time: a chunk of 256 points is added in one go
+// whenever NO addition of the sequential walk through that chunk can round — then the walk's result is the exact sum,
+// which a tree computes just as well.  Sufficient condition per axis: with S the running sum, every partial sum is
+// bounded by M = |S| + sum|v| < 2^K and every operand is a multiple of 2^q (q = lowest set bit of S, float ulp of the
+// smallest non-zero |v|), so all partial sums are multiples of 2^q below 2^K: exactly representable when K - q <= 53.
+// Chunks that fail the test (a coordinate within millimetres of zero next to a large running sum) are walked in order.
+constexpr int CEN_U = 8;  // points per lane per chunk
+
+__device__ __forceinline__ int lowbit_exp(double s) {  // exponent of the lowest set bit of a finite double; 4096 for 0
+  const unsigned long long b = (unsigned long long)__double_as_longlong(s);
+  const int e = (int)((b >> 52) & 0x7ffull);
+  unsigned long long m = b & 0xfffffffffffffull;
+  if (e == 0 && m == 0ull) return 4096;
+  if (e != 0) m |= 1ull << 52;
+  return (e == 0 ? -1074 : e - 1075) + (__ffsll((long long)m) - 1);
+}
+
+__device__ __forceinline__ int dexp(double x) {  // floor(log2 |x|) of a normal double (the operands here are float-derived)
+  return (int)(((unsigned long long)__double_as_longlong(x) >> 52) & 0x7ffull) - 1023;
+}
+
 __global__ void __launch_bounds__(32) k_centroid(const BuildJob *__restrict__ jobs, const int *__restrict__ which, double *__restrict__ out) {
   const BuildJob &j = jobs[which[blockIdx.x]];
   const int lane = threadIdx.x;
-  // The sums are order dependent (every addition rounds), so they are taken in point order by ONE lane; the other
-  // lanes fetch (coalesced, two chunks ahead), filter and convert 32 points at a time into shared memory.
-  __shared__ double sx[2][32], sy[2][32], sz[2][32];
-  __shared__ unsigned smask[2];
-  double ax = 0, ay = 0, az = 0;
+  double S[3] = {0.0, 0.0, 0.0};
   long long cnt = 0;
-  float4 nxt = make_float4(0, 0, 0, 0);
-  if (lane < j.npts) nxt = j.pts[lane];
-  int buf = 0;
-  for (int base = 0; base < j.npts; base += 32, buf ^= 1) {
-    const float4 p = nxt;
-    const int i = base + lane;
-    if (i + 32 < j.npts) nxt = j.pts[i + 32];
-    const bool use = i < j.npts && !pt_skip(p, j.range_limit);
-    sx[buf][lane] = (double)p.x, sy[buf][lane] = (double)p.y, sz[buf][lane] = (double)p.z;
-    const unsigned m = __ballot_sync(FULL, use);
-    if (lane == 0) smask[buf] = m;
-    __syncwarp();
-    if (lane == 0) {
-      if (m == FULL) {
+  for (int base = 0; base < j.npts; base += 32 * CEN_U) {
+    double v[3][CEN_U];
+    unsigned use = 0;
 #pragma unroll
-        for (int r = 0; r < 32; r++) ax += sx[buf][r], ay += sy[buf][r], az += sz[buf][r];
-        cnt += 32;
-      } else {
-        for (int r = 0; r < 32; r++)
-          if (m >> r & 1u) ax += sx[buf][r], ay += sy[buf][r], az += sz[buf][r], cnt++;
+    for (int u = 0; u < CEN_U; u++) {
+      const int i = base + u * 32 + lane;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < j.npts) p = j.pts[i];
+      const bool ok = i < j.npts && !pt_skip(p, j.range_limit);
+      use |= ok ? (1u << u) : 0u;
+      v[0][u] = ok ? (double)p.x : 0.0, v[1][u] = ok ? (double)p.y : 0.0, v[2][u] = ok ? (double)p.z : 0.0;
+    }
+    cnt += __reduce_add_sync(FULL, __popc(use));
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      double L = 0.0, AB = 0.0, mn = 1.7976931348623157e308;
+#pragma unroll
+      for (int u = 0; u < CEN_U; u++) {
+        const double x = v[a][u], ax = fabs(x);
+        L += x;
+        AB = __dadd_ru(AB, ax);  // rounded up: M below is a true upper bound
+        mn = (ax != 0.0 && ax < mn) ? ax : mn;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        L += __shfl_xor_sync(FULL, L, off);
+        AB = __dadd_ru(AB, __shfl_xor_sync(FULL, AB, off));
+        const double o = __shfl_xor_sync(FULL, mn, off);
+        mn = o < mn ? o : mn;
+      }
+      const double M = __dadd_ru(fabs(S[a]), AB);  // >= |any partial sum| of the walk through this chunk
+      bool exact = M < 1e300;                      // finite
+      if (exact && AB != 0.0) {
+        int q = dexp(mn) - 23;  // float ulp of the smallest non-zero addend
+        const int qs = lowbit_exp(S[a]);
+        q = qs < q ? qs : q;
+        exact = dexp(M) - q <= 52;  // M < 2^(q+53): every multiple of 2^q up to M is a double
+      }
+      if (exact) {
+        S[a] += L;  // = the sequential result (no rounding anywhere)
+      } else {      // walk the chunk in point order: i = base + u*32 + lane
+        double s = S[a];
+#pragma unroll
+        for (int u = 0; u < CEN_U; u++) {
+          const unsigned um = __ballot_sync(FULL, (use >> u) & 1u);
+          for (int l = 0; l < 32; l++) {
+            const double x = __shfl_sync(FULL, v[a][u], l);
+            if ((um >> l) & 1u) s += x;
+          }
+        }
+        S[a] = s;
       }
     }
-    // double buffering: the next chunk is written to the other buffer while lane 0 may still be adding
   }
   if (lane == 0) {
     double *o = out + (size_t)blockIdx.x * 8;
     o[3] = (double)cnt;
-    if (cnt > 0) o[0] = ax / (double)cnt, o[1] = ay / (double)cnt, o[2] = az / (double)cnt;
+    if (cnt > 0) o[0] = S[0] / (double)cnt, o[1] = S[1] / (double)cnt, o[2] = S[2] / (double)cnt;
     unsigned long long *k = reinterpret_cast<unsigned long long *>(o);
     k[4] = 0ull;   // maxDist = +0.0
     k[5] = 0ull;   // ordered key of the smallest value
@@ -207,9 +256,12 @@ __global__ void k_scatter(const BuildJob *__restrict__ jobs) {
 
 // ---- per-cell Gaussians --------------------------------------------------------------------------------
 // NDTCell::rescaleCovariance [upstream]: any eigenvalue <= 0 -> no Gaussian; clamp to >= max/1000 (fixture-pinned)
-__device__ bool rescale_covariance(double *cov) {
+// max_sweeps < 64: *deferred is set (and cov left untouched) when the Jacobi iteration needs more sweeps than that
+__device__ bool rescale_covariance(double *cov, int max_sweeps = 64, bool *deferred = nullptr) {
   double ev[3], V[9];
-  eig_sym_n<3>(cov, ev, V);
+  const bool done = eig_sym_n<3>(cov, ev, V, max_sweeps);
+  if (deferred) *deferred = !done;
+  if (!done) return false;
   if (ev[0] <= 0 || ev[1] <= 0 || ev[2] <= 0) return false;
   double maxe = ev[0] > ev[1] ? ev[0] : ev[1];
   maxe = maxe > ev[2] ? maxe : ev[2];
@@ -322,9 +374,12 @@ __global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restric
 }
 
 // (b) one THREAD per cell: sequential mean and scatter matrix over its points in id order (the operation order of
-// NDTCell::computeGaussian), merge with the stored (N, mean, cov), occupancy, eigen clamp.
+// NDTCell::computeGaussian), merge with the stored (N, mean, cov), occupancy.  Cells whose covariance has to go through
+// rescaleCovariance are appended to the map's eigen list (the dead `cursor` array) and finished by k_eigen: the 3x3
+// Jacobi iteration is a long serial fp64 chain that wants many resident warps, the gather loops here want registers.
 __global__ void __launch_bounds__(128) k_cells(const BuildJob *__restrict__ jobs) {
   const BuildJob &j = jobs[blockIdx.y];
+  const float4 *__restrict__ pts = j.pts;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < j.n_all; c += gridDim.x * blockDim.x) {
     const int key = j.cell_key[c];
     const int b = key >> 6, bit = key & 63;
@@ -341,8 +396,9 @@ __global__ void __launch_bounds__(128) k_cells(const BuildJob *__restrict__ jobs
       }
     }
     const int n = j.cnt[c];
+    bool eigen = false;
     if (n > 0) {
-      const int *ids = j.seg2 + j.seg_off[c];
+      const int *__restrict__ ids = j.seg2 + j.seg_off[c];
       {  // occupancy: += n*log(0.6/0.4), clamped (NDTCell::updateOccupancy)
         float o2 = occ + (float)((double)n * j.log_occ);
         o2 = o2 > j.occ_limit ? j.occ_limit : o2;
@@ -350,46 +406,107 @@ __global__ void __launch_bounds__(128) k_cells(const BuildJob *__restrict__ jobs
         occ = o2;
       }
       if (has || n >= 3) {
+        // the additions stay in id order; the gathers of four points are issued together
         double ms0 = 0, ms1 = 0, ms2 = 0;
-        for (int q = 0; q < n; q++) {
-          const float4 p = j.pts[ids[q]];
+        int q = 0;
+        for (; q + 4 <= n; q += 4) {
+          const float4 p0 = pts[ids[q]], p1 = pts[ids[q + 1]], p2 = pts[ids[q + 2]], p3 = pts[ids[q + 3]];
+          ms0 += (double)p0.x, ms1 += (double)p0.y, ms2 += (double)p0.z;
+          ms0 += (double)p1.x, ms1 += (double)p1.y, ms2 += (double)p1.z;
+          ms0 += (double)p2.x, ms1 += (double)p2.y, ms2 += (double)p2.z;
+          ms0 += (double)p3.x, ms1 += (double)p3.y, ms2 += (double)p3.z;
+        }
+        for (; q < n; q++) {
+          const float4 p = pts[ids[q]];
           ms0 += (double)p.x, ms1 += (double)p.y, ms2 += (double)p.z;
         }
         const double ml0 = ms0 / (double)n, ml1 = ms1 / (double)n, ml2 = ms2 / (double)n;
         double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-        for (int q = 0; q < n; q++) {
-          const float4 p = j.pts[ids[q]];
+        q = 0;
+        for (; q + 2 <= n; q += 2) {
+          const float4 p0 = pts[ids[q]], p1 = pts[ids[q + 1]];
+          const double d0 = (double)p0.x - ml0, d1 = (double)p0.y - ml1, d2 = (double)p0.z - ml2;
+          const double e0 = (double)p1.x - ml0, e1 = (double)p1.y - ml1, e2 = (double)p1.z - ml2;
+          c00 += d0 * d0, c01 += d0 * d1, c02 += d0 * d2, c11 += d1 * d1, c12 += d1 * d2, c22 += d2 * d2;
+          c00 += e0 * e0, c01 += e0 * e1, c02 += e0 * e2, c11 += e1 * e1, c12 += e1 * e2, c22 += e2 * e2;
+        }
+        for (; q < n; q++) {
+          const float4 p = pts[ids[q]];
           const double d0 = (double)p.x - ml0, d1 = (double)p.y - ml1, d2 = (double)p.z - ml2;
           c00 += d0 * d0, c01 += d0 * d1, c02 += d0 * d2, c11 += d1 * d1, c12 += d1 * d2, c22 += d2 * d2;
         }
         const double ms[3] = {ms0, ms1, ms2}, ml[3] = {ml0, ml1, ml2};
         const double csum[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22};
         if (!has) {
-          for (int q = 0; q < 3; q++) mean[q] = ml[q];
-          for (int q = 0; q < 9; q++) cov[q] = csum[q] / (double)(n - 1);
+          for (int q2 = 0; q2 < 3; q2++) mean[q2] = ml[q2];
+          for (int q2 = 0; q2 < 9; q2++) cov[q2] = csum[q2] / (double)(n - 1);
           N = n;
         } else {  // pairwise (Chan) merge with the stored (N, mean, cov)
           const double N0 = (double)N, n1 = (double)n;
           double mS[3], cS[9], tv[3];
-          for (int q = 0; q < 3; q++) mS[q] = mean[q] * N0;
-          for (int q = 0; q < 9; q++) cS[q] = cov[q] * (N0 - 1.0);
+          for (int q2 = 0; q2 < 3; q2++) mS[q2] = mean[q2] * N0;
+          for (int q2 = 0; q2 < 9; q2++) cS[q2] = cov[q2] * (N0 - 1.0);
           const double w = N0 / (n1 * (N0 + n1));
-          for (int q = 0; q < 3; q++) tv[q] = (n1 / N0) * mS[q] - ms[q];
+          for (int q2 = 0; q2 < 3; q2++) tv[q2] = (n1 / N0) * mS[q2] - ms[q2];
           for (int a = 0; a < 3; a++)
             for (int bb = 0; bb < 3; bb++) cS[a * 3 + bb] += csum[a * 3 + bb] + w * tv[a] * tv[bb];
-          for (int q = 0; q < 3; q++) mS[q] += ms[q];
+          for (int q2 = 0; q2 < 3; q2++) mS[q2] += ms[q2];
           double Nt = N0 + n1;
-          for (int q = 0; q < 3; q++) mean[q] = mS[q] / Nt;
-          for (int q = 0; q < 9; q++) cov[q] = cS[q] / (Nt - 1.0);
+          for (int q2 = 0; q2 < 3; q2++) mean[q2] = mS[q2] / Nt;
+          for (int q2 = 0; q2 < 9; q2++) cov[q2] = cS[q2] / (Nt - 1.0);
           if (Nt > (double)j.maxnumpoints) Nt = (double)j.maxnumpoints;
           N = (int)Nt;
         }
-        has = rescale_covariance(cov) ? 1 : 0;
+        eigen = true;
+        has = 0;  // decided by k_eigen
       }
     }
     for (int q = 0; q < 3; q++) j.cmean[(size_t)c * 3 + q] = mean[q];
     for (int q = 0; q < 9; q++) j.ccov[(size_t)c * 9 + q] = cov[q];
     j.cn[c] = N, j.chas[c] = has, j.cocc[c] = occ;
+    if (eigen) j.cursor[atomicAdd(j.counts + 5, 1)] = c;
+  }
+}
+
+// (c) one thread per listed cell: NDTCell::rescaleCovariance (eigen clamp), decides hasGaussian_.  Almost every cell
+// converges in 2-4 Jacobi sweeps; the ~2 % with an exactly singular covariance (collinear points) never meet the
+// stopping test and run the full 64 sweeps — in a warp of 32 cells one of them would make the other 31 wait 20x longer,
+// so the first pass stops after EIG_FAST_SWEEPS and defers those cells to a compact second list (the dead `cell_key`
+// array) that k_eigen_hard works through with full warps.  Same operations per cell either way: bit-identical results.
+constexpr int EIG_FAST_SWEEPS = 8;
+
+__global__ void __launch_bounds__(128, 6) k_eigen(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  const int n = j.counts[5];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int c = j.cursor[t];
+    double cov[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) cov[q] = j.ccov[(size_t)c * 9 + q];
+    bool deferred;
+    const bool ok = rescale_covariance(cov, EIG_FAST_SWEEPS, &deferred);
+    if (deferred) {
+      j.cell_key[atomicAdd(j.counts + 6, 1)] = c;
+      continue;
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++) j.ccov[(size_t)c * 9 + q] = cov[q];
+    j.chas[c] = ok ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(128, 6) k_eigen_hard(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  const int n = j.counts[6];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int c = j.cell_key[t];
+    double cov[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) cov[q] = j.ccov[(size_t)c * 9 + q];
+    const bool ok = rescale_covariance(cov);
+#pragma unroll
+    for (int q = 0; q < 9; q++) j.ccov[(size_t)c * 9 + q] = cov[q];
+    j.chas[c] = ok ? 1 : 0;
   }
 }
 
@@ -610,7 +727,9 @@ int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int ma
   k_scatter<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
   k_sort_segments<<<dim3(chunks_for(max_ntb, 8), n), 256, 0, s>>>(d_jobs);
   k_cells<<<dim3(chunks_for(max_cells, 128), n), 128, 0, s>>>(d_jobs);
-  return 5;
+  k_eigen<<<dim3(chunks_for(max_cells, 128), n), 128, 0, s>>>(d_jobs);
+  k_eigen_hard<<<dim3(chunks_for(max_cells / 16 + 1, 128), n), 128, 0, s>>>(d_jobs);
+  return 7;
 }
 int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s) {
   k_gscan<<<n, 1024, 0, s>>>(d_jobs);

@@ -122,20 +122,27 @@ NDTB_HDF inline double robust_yaw(const Pose &P) {
 
 // cyclic Jacobi, symmetric n x n (n<=6), eigenvalues ascending, eigenvectors in the columns of V.
 // Compile-time n: every loop unrolls and the 3x3 instance (one per NDT cell) lives in registers.
+// max_sweeps < 64 is for callers that defer the rare non-converging matrices (exactly singular ones never meet the
+// stopping test and run all 64 sweeps): returns false when the sweep cap was hit before the stopping test passed; the
+// result is then NOT the 64-sweep result and must be recomputed with the full cap.
 template <int n>
-NDTB_HDF inline void eig_sym_n(const double *Ain, double *evals, double *V) {
+NDTB_HDF inline bool eig_sym_n(const double *Ain, double *evals, double *V, int max_sweeps = 64) {
   double A[n * n];
   for (int i = 0; i < n * n; i++) A[i] = Ain[i];
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 64; sweep++) {
+  bool converged = max_sweeps >= 64;
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
     double off = 0, diag = 0;
     for (int i = 0; i < n; i++)
       for (int j = 0; j < n; j++) {
         const double a2 = A[i * n + j] * A[i * n + j];
         if (i == j) diag += a2; else off += a2;
       }
-    if (off <= 1e-32 * diag || off == 0.0) break;
+    if (off <= 1e-32 * diag || off == 0.0) {
+      converged = true;
+      break;
+    }
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -187,6 +194,7 @@ NDTB_HDF inline void eig_sym_n(const double *Ain, double *evals, double *V) {
     }
   }
   for (int i = 0; i < n * n; i++) V[i] = Vt[i];
+  return converged;
 }
 NDTB_HDF inline void eig_sym(int n, const double *Ain, double *evals, double *V) {
   if (n == 3) eig_sym_n<3>(Ain, evals, V);

@@ -350,3 +350,41 @@ def test_p2d_derivatives_and_match(oracle, engine, c1, c2small):
     assert no == ng and _rel(sg, so) < 1e-10 and _rel(gg, go) < 1e-9
     r = m.match(gm[0], np.zeros((0, 4), np.float32), D)
     assert r.pose_changed == 0
+
+
+def test_centroid_bit_exact_on_hostile_clouds(oracle, engine):
+    """The guess-size grid centre is the point-order centroid.  The kernel adds 256-point chunks at once when it can
+    prove that no sequential addition rounds, and walks the chunk in order otherwise: both paths must give the oracle's
+    bits, also when magnitudes differ by 12 decades, when coordinates sit next to zero and with NaN / range drops."""
+    import ndt_feature_graph_b200 as N
+
+    rng = np.random.default_rng(7)
+    clouds = []
+    n = 5000
+    base = rng.uniform(-60, 60, size=(n, 3))
+    clouds.append(base)                                            # plain
+    tiny = base.copy()
+    tiny[::3] *= 1e-7                                              # coordinates within micrometres of zero
+    clouds.append(tiny)
+    big = base.copy()
+    big[:, 0] += 3.0e5                                             # a large running sum in x
+    big[::5, 0] = rng.uniform(-1e-6, 1e-6, size=big[::5, 0].shape)
+    clouds.append(big)
+    mixed = base * np.exp(rng.uniform(-14, 6, size=(n, 1)))        # 9 decades of magnitudes
+    mixed[::11, 2] = np.nan
+    clouds.append(mixed)
+    clouds.append(np.zeros((300, 3)))                              # all zeros
+    clouds.append(rng.uniform(-1, 1, size=(257, 3)))               # one full chunk + one point
+    for k, c in enumerate(clouds):
+        c4 = np.concatenate([c, np.zeros((c.shape[0], 1))], 1).astype(np.float32)
+        for rl in (-1.0, 40.0):
+            o = oracle.OracleMap(0.5)
+            o.set_map_size(60.0, 60.0, 6.0)
+            nb_o = o.load_point_cloud(c4, rl)
+            g = N.NDTMap(engine, 0.5)
+            g.setMapSize(60.0, 60.0, 6.0)
+            nb_g = g.loadPointCloud(c4, rl)
+            oc, _, osz = o.grid()
+            gc, _, gsz = g.grid()
+            assert np.array_equal(oc, gc), (k, rl, oc, gc)
+            assert np.array_equal(osz, gsz) and nb_o == nb_g

@@ -1,7 +1,5 @@
 #!/bin/bash
-# quick engine A/B on the GPU box: parity tests + match micro-benchmark at a few batch sizes
+# quick match-kernel A/B on the GPU box: cluster width x pass budget
 OUT=gpurun_out; mkdir -p $OUT
-(timeout 900 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests exit $?" >> $OUT/tests.log)
-tail -5 $OUT/tests.log
-for n in ${SIZES:-296 1 32 148}; do for c in ${ENGINES:--1 1}; do CTAS=$c timeout 300 python scripts/bench_match.py $n 3 2>&1 | tail -1 | cut -c1-330; done; done > $OUT/engine_ab.log
+for n in ${SIZES:-296}; do for c in ${ENGINES:-1 2 4}; do for b in ${BUDGETS:-0}; do echo -n "CTAS=$c BUDGET=$b "; CTAS=$c BUDGET=$b timeout 300 python scripts/bench_match.py $n 3 2>&1 | tail -1 | cut -c1-200; done; done; done > $OUT/engine_ab.log
 cat $OUT/engine_ab.log

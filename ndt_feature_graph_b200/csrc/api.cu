@@ -22,13 +22,13 @@ namespace ndtb {
 size_t match_smem_bytes(int table_entries);
 size_t opt_state_bytes();
 cudaError_t launch_match(const MatchJob *d_jobs, const int *d_job_ids, int n_slots, int cluster, const MatchConfig &cfg,
-                         ndtb_result *d_out, void *d_states, int resume, int pass_budget, int *d_unfinished,
+                         ndtb_result *d_out, void *d_states, int resume, int pass_budget, int *d_unfinished, int *d_yielded,
                          cudaStream_t stream);
 cudaError_t launch_derivatives(const MatchJob *d_job, const MatchConfig &cfg, bool hess, int n_ctas, double *d_partial,
                                double *d_out29, cudaStream_t stream);
 cudaError_t launch_covariance(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, const ndtb_result *d_res,
                               const long long *d_gt_off, double *d_gt, double *d_partial, int n_chunks, double *d_cov36,
-                              int *d_status, cudaStream_t stream);
+                              int *d_status, const int *d_yielded, int mode, cudaStream_t stream);
 int cov_partial_width();
 int acc_total();
 }  // namespace ndtb
@@ -48,6 +48,10 @@ struct ndtb_ctx {
   // host-buffer path: scans are uploaded on a second stream in chunks while the previous chunk's maps are being built
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> copy_events;
+  // batched match: the covariance of the registrations that finished in the first launch runs on this stream while the
+  // second launch (stragglers, about half of the SMs) is still working
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_ev[2] = {nullptr, nullptr};
 };
 
 #define CU_TRY(ctx, expr)                                                                           \
@@ -522,43 +526,68 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
   auto pow2_floor = [](int v) { int p = 1; while (2 * p <= v) p <<= 1; return p; };
   int G1 = p->ctas_per_match > 0 ? pow2_floor(std::min(p->ctas_per_match, 8)) : ((int64_t)2 * n >= sms ? 1 : pow2_floor((int)std::min<int64_t>(8, sms / n)));
   int budget = p->pass_budget > 0 ? p->pass_budget : (p->pass_budget < 0 ? 0 : (((int64_t)n * G1 >= sms) ? 64 : 0));
-  const size_t o_states = c.take(budget > 0 ? opt_state_bytes() * (size_t)n : 0), o_unf = c.take(4 * (size_t)(n + 1));
+  const size_t o_states = c.take(budget > 0 ? opt_state_bytes() * (size_t)n : 0), o_unf = c.take(4 * (size_t)(2 * n + 1));
   SlabP s;
   if (int rc = slab_alloc(ctx, c.off, s)) return rc;
   MatchJob *d_jobs = (MatchJob *)(s->p + o_jobs);
   ndtb_result *d_res = out_mem == NDTB_MEM_DEVICE ? res : (ndtb_result *)(s->p + o_res);
+  const bool do_cov = with_cov && cov36s;
+  double *d_cov = do_cov ? (out_mem == NDTB_MEM_DEVICE ? cov36s : (double *)(s->p + o_cov)) : nullptr;
   CU_TRY(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(MatchJob) * n, cudaMemcpyHostToDevice, st));
+  if (do_cov) {
+    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_goff, gt_off.data(), 8 * n, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemsetAsync(s->p + o_gt, 0, 48 * gt_total, st));
+  }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->timing) {
     CU_TRY(ctx, cudaEventCreate(&ev0));
     CU_TRY(ctx, cudaEventCreate(&ev1));
     CU_TRY(ctx, cudaEventRecord(ev0, st));
   }
-  int *d_unf = (int *)(s->p + o_unf);
-  if (budget > 0) CU_TRY(ctx, cudaMemsetAsync(d_unf, 0, 4, st));
-  CU_TRY(ctx, launch_match(d_jobs, nullptr, (int)n, G1, cfg, d_res, s->p + o_states, 0, budget, d_unf, st));
+  int *d_unf = (int *)(s->p + o_unf), *d_yielded = d_unf + 1 + n;
+  if (budget > 0) CU_TRY(ctx, cudaMemsetAsync(d_unf, 0, 4 * (size_t)(2 * n + 1), st));
+  CU_TRY(ctx, launch_match(d_jobs, nullptr, (int)n, G1, cfg, d_res, s->p + o_states, 0, budget, d_unf, budget > 0 ? d_yielded : nullptr, st));
   ctx->launches += 1;
+  bool cov_split = false;
   if (budget > 0) {
     int n_unf = 0;
     CU_TRY(ctx, cudaMemcpyAsync(&n_unf, d_unf, 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
     if (n_unf > 0) {
+      if (do_cov) {
+        if (!ctx->aux_stream) {
+          CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+          for (cudaEvent_t &e : ctx->aux_ev) CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->aux_ev[0], st));  // first launch complete
+      }
       const int G2 = pow2_floor(std::min(8, std::max(1, sms / n_unf)));
-      CU_TRY(ctx, launch_match(d_jobs, d_unf + 1, n_unf, G2, cfg, d_res, s->p + o_states, 1, 0, d_unf, st));
+      CU_TRY(ctx, launch_match(d_jobs, d_unf + 1, n_unf, G2, cfg, d_res, s->p + o_states, 1, 0, d_unf, nullptr, st));
       ctx->launches += 1;
+      if (do_cov) {
+        // Covariance of everything that is already final, on the second stream, concurrently with the finishing launch.
+        // Enqueued AFTER it: the finishing launch's clusters (whole SMs) are placed first, the covariance CTAs fill
+        // the SMs it leaves free.
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
+        CU_TRY(ctx, launch_covariance(d_jobs, (int)n, cfg, d_res, (const long long *)(s->p + o_goff), (double *)(s->p + o_gt),
+                                      (double *)(s->p + o_part), n_chunks, d_cov, (int *)(s->p + o_stat), d_yielded, 1,
+                                      ctx->aux_stream));
+        CU_TRY(ctx, cudaEventRecord(ctx->aux_ev[1], ctx->aux_stream));
+        ctx->launches += 2;
+        cov_split = true;
+      }
     }
   }
   if (ctx->timing) {
     CU_TRY(ctx, cudaEventRecord(ev1, st));
     ctx->timed.push_back({ev0, ev1});
   }
-  if (with_cov && cov36s) {
-    double *d_cov = out_mem == NDTB_MEM_DEVICE ? cov36s : (double *)(s->p + o_cov);
-    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_goff, gt_off.data(), 8 * n, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemsetAsync(s->p + o_gt, 0, 48 * gt_total, st));
+  if (do_cov) {
     CU_TRY(ctx, launch_covariance(d_jobs, (int)n, cfg, d_res, (const long long *)(s->p + o_goff), (double *)(s->p + o_gt),
-                                  (double *)(s->p + o_part), n_chunks, d_cov, (int *)(s->p + o_stat), st));
+                                  (double *)(s->p + o_part), n_chunks, d_cov, (int *)(s->p + o_stat), d_yielded,
+                                  cov_split ? 2 : 0, st));
     ctx->launches += 2;
+    if (cov_split) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[1], 0));
     if (out_mem != NDTB_MEM_DEVICE)
       CU_TRY(ctx, cudaMemcpyAsync(cov36s, d_cov, 288 * (size_t)n, cudaMemcpyDeviceToHost, st));
   }
@@ -624,6 +653,9 @@ void ndtb_ctx_destroy(ndtb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream), cudaStreamDestroy(ctx->copy_stream);
   for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream), cudaStreamDestroy(ctx->aux_stream);
+  for (cudaEvent_t e : ctx->aux_ev)
+    if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1066,7 +1098,7 @@ int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src,
   CU_TRY(ctx, cudaMemcpyAsync(s->p + o_job, &j, sizeof j, cudaMemcpyHostToDevice, st));
   CU_TRY(ctx, launch_covariance((MatchJob *)(s->p + o_job), 1, cfg, nullptr, (const long long *)(s->p + o_goff),
                                 (double *)(s->p + o_gt), (double *)(s->p + o_part), n_chunks, (double *)(s->p + o_cov),
-                                (int *)(s->p + o_stat), st));
+                                (int *)(s->p + o_stat), nullptr, 0, st));
   ctx->launches += 2;
   int status = 0;
   CU_TRY(ctx, cudaMemcpyAsync(cov36, s->p + o_cov, 288, cudaMemcpyDeviceToHost, st));

@@ -400,7 +400,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // state and is finished by a second launch with a wider cluster.
 __global__ void __launch_bounds__(MATCH_THREADS, 1)
 match_kernel(const MatchJob *__restrict__ jobs, const int *__restrict__ job_ids, MatchConfig cfg, ndtb_result *__restrict__ out,
-             OptState *__restrict__ states, int resume, int pass_budget, int *__restrict__ unfinished /*[0]=count, ids follow*/) {
+             OptState *__restrict__ states, int resume, int pass_budget, int *__restrict__ unfinished /*[0]=count, ids follow*/,
+             int *__restrict__ yielded /*[n jobs] set to 1 for a registration handed to the finishing launch*/) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned G = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
@@ -499,6 +500,7 @@ match_kernel(const MatchJob *__restrict__ jobs, const int *__restrict__ job_ids,
       out[jid].kernel_ms = ms;  // carried over to the finishing launch
       const int at = atomicAdd(unfinished, 1);
       unfinished[1 + at] = jid;
+      if (yielded) yielded[jid] = 1;
     } else {
       ndtb_result r;
       pose_to_cm(s.T, r.T);
@@ -526,7 +528,7 @@ size_t opt_state_bytes() { return sizeof(OptState); }
 
 // n_slots registrations (job_ids[slot] or slot itself), each on a cluster of `cluster` CTAs
 cudaError_t launch_match(const MatchJob *d_jobs, const int *d_job_ids, int n_slots, int cluster, const MatchConfig &cfg,
-                         ndtb_result *d_out, void *d_states, int resume, int pass_budget, int *d_unfinished,
+                         ndtb_result *d_out, void *d_states, int resume, int pass_budget, int *d_unfinished, int *d_yielded,
                          cudaStream_t stream) {
   const size_t smem = match_smem_bytes(cfg.table_smem_entries);
   cudaError_t e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -541,7 +543,7 @@ cudaError_t launch_match(const MatchJob *d_jobs, const int *d_job_ids, int n_slo
   at[0].val.clusterDim.x = (unsigned)cluster, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
   lc.attrs = at, lc.numAttrs = 1;
   return cudaLaunchKernelEx(&lc, match_kernel, d_jobs, d_job_ids, cfg, d_out, (OptState *)d_states, resume, pass_budget,
-                            d_unfinished);
+                            d_unfinished, d_yielded);
 }
 
 // ------------------------------------------------------------------ stand-alone derivativesNDT (API + tests)
@@ -615,7 +617,9 @@ __device__ __forceinline__ void outer_upper(const double *g, double *o) {
 // grid (chunks, jobs): thread per source cell, hits processed serially; per-target sums by fp64 atomics.
 __global__ void __launch_bounds__(COV_THREADS)
 cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_result *__restrict__ res,
-                const long long *__restrict__ gt_off, double *__restrict__ gt, double *__restrict__ partial) {
+                const long long *__restrict__ gt_off, double *__restrict__ gt, double *__restrict__ partial,
+                const int *__restrict__ yielded, int mode /*0 all, 1 not yielded, 2 yielded only*/) {
+  if (mode && (yielded[blockIdx.y] != 0) != (mode == 2)) return;
   const MatchJob &job = jobs[blockIdx.y];
   __shared__ double P[12];
   __shared__ GridDesc grid;
@@ -696,7 +700,8 @@ cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_r
 __global__ void __launch_bounds__(COV_THREADS)
 cov_finalize_kernel(const MatchJob *__restrict__ jobs, const ndtb_result *__restrict__ res, const long long *__restrict__ gt_off,
                     const double *__restrict__ gt, const double *__restrict__ partial, int n_chunks,
-                    double *__restrict__ cov36, int *__restrict__ status) {
+                    double *__restrict__ cov36, int *__restrict__ status, const int *__restrict__ yielded, int mode) {
+  if (mode && (yielded[blockIdx.x] != 0) != (mode == 2)) return;
   const MatchJob &job = jobs[blockIdx.x];
   __shared__ double tot[COV_W];
   __shared__ double red[(COV_THREADS / 32) * 21];
@@ -760,11 +765,11 @@ cov_finalize_kernel(const MatchJob *__restrict__ jobs, const ndtb_result *__rest
 
 cudaError_t launch_covariance(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, const ndtb_result *d_res,
                               const long long *d_gt_off, double *d_gt, double *d_partial, int n_chunks,
-                              double *d_cov36, int *d_status, cudaStream_t stream) {
+                              double *d_cov36, int *d_status, const int *d_yielded, int mode, cudaStream_t stream) {
   dim3 grid(n_chunks, n_jobs);
-  cov_pass_kernel<<<grid, COV_THREADS, 0, stream>>>(d_jobs, cfg, d_res, d_gt_off, d_gt, d_partial);
+  cov_pass_kernel<<<grid, COV_THREADS, 0, stream>>>(d_jobs, cfg, d_res, d_gt_off, d_gt, d_partial, d_yielded, mode);
   cov_finalize_kernel<<<n_jobs, COV_THREADS, 0, stream>>>(d_jobs, d_res, d_gt_off, d_gt, d_partial, n_chunks, d_cov36,
-                                                         d_status);
+                                                         d_status, d_yielded, mode);
   return cudaGetLastError();
 }
 

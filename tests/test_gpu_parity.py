@@ -388,3 +388,30 @@ def test_centroid_bit_exact_on_hostile_clouds(oracle, engine):
             gc, _, gsz = g.grid()
             assert np.array_equal(oc, gc), (k, rl, oc, gc)
             assert np.array_equal(osz, gsz) and nb_o == nb_g
+
+
+def test_pass_budget_handover_with_split_covariance(oracle, engine, c2small):
+    """A pass budget forces the two-launch path (registrations over budget are finished by a second launch on wider
+    clusters) and with it the split covariance (finished registrations on a second stream while the stragglers run).
+    Results must be the ones of the single-launch path."""
+    import ndt_feature_graph_b200 as N
+
+    ca, cb, D, om, gm = c2small
+    T0s = [synth.perturb_pose(D, 100 + i, dt=0.5 if i % 4 == 0 else 0.15, dr=0.08 if i % 4 == 0 else 0.03) for i in range(16)]
+    n = len(T0s)
+    rb, cb_ = engine.match_batch([gm[0]] * n, [gm[1]] * n, T0s, engine.default_params(ctas_per_match=1, pass_budget=10),
+                                 with_covariance=True)
+    r1, c1_ = engine.match_batch([gm[0]] * n, [gm[1]] * n, T0s, engine.default_params(ctas_per_match=1, pass_budget=-1),
+                                 with_covariance=True)
+    assert (rb["n_exec_passes"] > 10).sum() >= 4 and (rb["n_exec_passes"] <= 10).sum() >= 1  # both groups exist
+    for i in range(n):
+        # cluster width differs between the launches (1 vs up to 8 CTAs): another summation order, same optimum
+        ro = oracle.d2d_match(om[0], om[1], T0s[i])
+        if not _oracle_is_stable(oracle, om[0], om[1], T0s[i], ro):
+            continue
+        assert synth.pose_error(rb["T"][i].reshape(4, 4).T, r1["T"][i].reshape(4, 4).T) < POSE_TIGHT
+        assert synth.pose_error(rb["T"][i].reshape(4, 4).T, ro.pose()) < POSE_TIGHT
+        np.testing.assert_allclose(cb_[i], c1_[i], rtol=1e-5, atol=1e-9 * np.abs(c1_[i]).max())
+        if ro.pose_changed:
+            _, co = oracle.d2d_covariance(om[0], om[1], ro.pose())
+            np.testing.assert_allclose(cb_[i], co, rtol=1e-5, atol=1e-9 * np.abs(co).max())

@@ -88,7 +88,8 @@ def cpu_registrations(tg, sr, T0s, threads, check_stability=0):
     """Times the oracle (restated reference algorithm) on the given pairs with `threads` host threads (one pair per
     thread at a time, like an OpenMP loop over edges).  Returns (seconds, results).  For the first `check_stability`
     pairs the match is repeated (untimed) with 3 OpenMP partial sums inside derivativesNDT — upstream's N_THREADS
-    summation order — to tell whether the reference algorithm reproduces ITSELF on that pair (DESIGN.md "Parity")."""
+    summation order — and with the initial guess nudged by one ulp, to tell whether the reference algorithm reproduces
+    ITSELF on that pair (oracle_py.d2d_is_stable, DESIGN.md "Parity")."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     from concurrent.futures import ThreadPoolExecutor
@@ -116,12 +117,11 @@ def cpu_registrations(tg, sr, T0s, threads, check_stability=0):
         out = list(ex.map(one, range(len(tg))))
     dt = time.perf_counter() - t0
 
-    def again(i):
-        r3 = O.d2d_match(keep[i][0], keep[i][1], T0s[i], O.default_params(n_threads=3))
-        return r3.pose()
+    def again(i):  # True when the oracle reproduces itself (other summation order, 1-ulp nudges of the initial guess)
+        return O.d2d_is_stable(keep[i][0], keep[i][1], T0s[i])
 
     if check_stability:
-        with ThreadPoolExecutor(max_workers=max(1, threads // 3)) as ex:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
             alt = list(ex.map(again, range(min(check_stability, len(tg)))))
         return dt, out, alt
     return dt, out
@@ -333,7 +333,7 @@ def run_gpu(args):
             errs = np.array([synth.pose_error(out[i][0], res["T"][i].reshape(4, 4).T) for i in range(ns)])
             # a pair pins parity only if the reference algorithm reproduces itself under its own (OpenMP) change of
             # summation order; basin-hopping registrations amplify 1-ulp differences to O(1) (DESIGN.md "Parity")
-            selfc = np.array([synth.pose_error(out[i][0], alt[i]) < 1e-9 for i in range(nchk)])
+            selfc = np.array(alt, dtype=bool)
             line["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {ns} scan pairs of the step (map build x2 + match + covariance), "
                                               f"one pair per host thread, {cores} threads, {dt:.1f} s"}

@@ -233,6 +233,29 @@ def p2d_match(tgt, pts, T0, params=None):
     return r
 
 
+def d2d_is_stable(tgt, src, T0, base=None, tol=1e-9, **kw):
+    """Does the reference algorithm reproduce ITSELF on this registration?  The optimiser is a chain of discontinuous
+    decisions (More-Thuente branches, neighbourhoods that change with the pose, best-pose fallback); on ill-conditioned
+    starts a 1-ulp change anywhere is amplified to O(1) in the result.  Upstream itself sums per OpenMP thread, so such a
+    registration has no single "reference answer" and cannot pin parity.  Stable = same pose (within tol) with
+    (a) 3 OpenMP partial sums inside derivativesNDT and (b) the initial translation nudged by one ulp, either way."""
+    from numpy import nextafter, inf
+
+    def err(ra, rb):
+        A, B = ra.pose(), rb.pose()
+        return max(abs(A - B).max(), 0.0)
+
+    r0 = base if base is not None else d2d_match(tgt, src, T0, default_params(**kw))
+    if err(r0, d2d_match(tgt, src, T0, default_params(n_threads=3, **kw))) > tol:
+        return False
+    for axis, direction in ((0, inf), (1, -inf), (2, inf)):
+        T = np.array(T0, dtype=np.float64).copy()
+        T[axis, 3] = nextafter(T[axis, 3], direction)
+        if err(r0, d2d_match(tgt, src, T, default_params(**kw))) > max(tol, 1e-9):
+            return False
+    return True
+
+
 def fusion_match(tgt, src, T0, Tcov, params=None):
     p = params or default_params(use_soft_constraints=1)
     r = Result()

@@ -217,13 +217,18 @@ int define_grids(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::
     }
     Carver c;
     const size_t o_j = c.take(sizeof(BuildJob) * W), o_gs = c.take(64 * (size_t)W), o_w = c.take(4 * (size_t)W);
+    std::vector<long long> rec_off((size_t)W + 1, 0);  // centroid chunk records (map_build.cu k_centroid_chunks)
+    for (int w = 0; w < W; w++) rec_off[w + 1] = rec_off[w] + (jobs[w].npts + centroid_chunk_points() - 1) / centroid_chunk_points();
+    const size_t o_ro = c.take(8 * (size_t)(W + 1)), o_rec = c.take(8 * (size_t)centroid_record_doubles() * (size_t)std::max<long long>(rec_off[W], 1));
     SlabP s;
     if (int rc = slab_alloc(ctx, c.off, s)) return rc;
     std::vector<double> gs(8 * (size_t)W);
     CU_TRY(ctx, cudaMemcpyAsync(s->p + o_j, jobs.data(), sizeof(BuildJob) * W, cudaMemcpyHostToDevice, st));
     CU_TRY(ctx, cudaMemcpyAsync(s->p + o_w, ident.data(), 4 * (size_t)W, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_ro, rec_off.data(), 8 * (size_t)(W + 1), cudaMemcpyHostToDevice, st));
     CU_TRY(ctx, cudaMemsetAsync(s->p + o_gs, 0, 64 * (size_t)W, st));
-    ctx->launches += launch_guess((const BuildJob *)(s->p + o_j), (const int *)(s->p + o_w), W, max_pts, (double *)(s->p + o_gs), st);
+    ctx->launches += launch_guess((const BuildJob *)(s->p + o_j), (const int *)(s->p + o_w), W, max_pts, (const long long *)(s->p + o_ro),
+                                  (double *)(s->p + o_rec), (double *)(s->p + o_gs), st);
     CU_TRY(ctx, cudaMemcpyAsync(gs.data(), s->p + o_gs, 64 * (size_t)W, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
     auto unkey = [](double bits) {

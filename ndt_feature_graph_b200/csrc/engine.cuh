@@ -47,8 +47,13 @@ __host__ __device__ __forceinline__ unsigned hash_block(int key, int tsize) {
 // LazyGrid::getIndexForPoint [upstream]: ind = floor((p - center)/cell + 0.5) + size/2.0 truncated to int.
 // Written with explicit round-to-nearest intrinsics so no FMA contraction can change a voxel index
 // relative to the CPU restatement (exact-index parity, SURVEY.md §7 hard part c).
+// A cell size that is a power of two (0.5 m in every shipped configuration) divides exactly: x / cell == x * (1/cell)
+// bit for bit, and the multiplication is one instruction where IEEE division is ~30.
 __device__ __forceinline__ bool voxel_axis(double p, double c, double cell, int size, int &out) {
-  const double v = __dadd_rn(floor(__dadd_rn(__ddiv_rn(__dsub_rn(p, c), cell), 0.5)), (double)size * 0.5);
+  const double d = __dsub_rn(p, c);
+  const bool pow2 = (__double_as_longlong(cell) & 0x000fffffffffffffll) == 0ll && cell > 1e-300 && cell < 1e300;
+  const double qd = pow2 ? __dmul_rn(d, __drcp_rn(cell)) : __ddiv_rn(d, cell);
+  const double v = __dadd_rn(floor(__dadd_rn(qd, 0.5)), (double)size * 0.5);
   if (!(v > -2147483000.0 && v < 2147483000.0)) return false;  // also rejects NaN
   out = __double2int_rz(v);
   return true;

@@ -39,7 +39,9 @@ __device__ __forceinline__ bool pt_skip(const float4 p, double range_limit) {
 // bounded by M = |S| + sum|v| < 2^K and every operand is a multiple of 2^q (q = lowest set bit of S, float ulp of the
 // smallest non-zero |v|), so all partial sums are multiples of 2^q below 2^K: exactly representable when K - q <= 53.
 // Chunks that fail the test (a coordinate within millimetres of zero next to a large running sum) are walked in order.
-constexpr int CEN_U = 8;  // points per lane per chunk
+constexpr int CEN_U = 8;                 // points per lane per chunk
+constexpr int CEN_CHUNK = 32 * CEN_U;    // 256 points
+constexpr int CEN_REC = 10;              // doubles per chunk record: 3 x (L, AB, mn) + count
 
 __device__ __forceinline__ int lowbit_exp(double s) {  // exponent of the lowest set bit of a finite double; 4096 for 0
   const unsigned long long b = (unsigned long long)__double_as_longlong(s);
@@ -49,67 +51,108 @@ __device__ __forceinline__ int lowbit_exp(double s) {  // exponent of the lowest
   if (e != 0) m |= 1ull << 52;
   return (e == 0 ? -1074 : e - 1075) + (__ffsll((long long)m) - 1);
 }
-
 __device__ __forceinline__ int dexp(double x) {  // floor(log2 |x|) of a normal double (the operands here are float-derived)
   return (int)(((unsigned long long)__double_as_longlong(x) >> 52) & 0x7ffull) - 1023;
 }
 
-__global__ void __launch_bounds__(32) k_centroid(const BuildJob *__restrict__ jobs, const int *__restrict__ which, double *__restrict__ out) {
-  const BuildJob &j = jobs[which[blockIdx.x]];
-  const int lane = threadIdx.x;
-  double S[3] = {0.0, 0.0, 0.0};
-  long long cnt = 0;
-  for (int base = 0; base < j.npts; base += 32 * CEN_U) {
-    double v[3][CEN_U];
-    unsigned use = 0;
+// (1) fully parallel: one warp per 256-point chunk.  Per axis: L = tree sum of the chunk (exact whenever the test in
+// (2) passes), AB = sum |v| rounded up, mn = smallest non-zero |v|; plus the number of usable points.
+__global__ void __launch_bounds__(128) k_centroid_chunks(const BuildJob *__restrict__ jobs, const int *__restrict__ which,
+                                                         const long long *__restrict__ rec_off, double *__restrict__ recs) {
+  const BuildJob &j = jobs[which[blockIdx.y]];
+  const int lane = threadIdx.x & 31;
+  const int nchunks = (j.npts + CEN_CHUNK - 1) / CEN_CHUNK;
+  for (int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks; ch += gridDim.x * (blockDim.x >> 5)) {
+    const int base = ch * CEN_CHUNK;
+    double L[3] = {0, 0, 0}, AB[3] = {0, 0, 0}, mn[3] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308};
+    int used = 0;
+    float4 p[CEN_U];
 #pragma unroll
     for (int u = 0; u < CEN_U; u++) {
       const int i = base + u * 32 + lane;
-      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < j.npts) p = j.pts[i];
-      const bool ok = i < j.npts && !pt_skip(p, j.range_limit);
-      use |= ok ? (1u << u) : 0u;
-      v[0][u] = ok ? (double)p.x : 0.0, v[1][u] = ok ? (double)p.y : 0.0, v[2][u] = ok ? (double)p.z : 0.0;
+      p[u] = i < j.npts ? j.pts[i] : make_float4(nanf(""), 0.f, 0.f, 0.f);
     }
-    cnt += __reduce_add_sync(FULL, __popc(use));
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-      double L = 0.0, AB = 0.0, mn = 1.7976931348623157e308;
+    for (int u = 0; u < CEN_U; u++) {
+      const bool ok = !pt_skip(p[u], j.range_limit);
+      used += ok;
+      const double v[3] = {ok ? (double)p[u].x : 0.0, ok ? (double)p[u].y : 0.0, ok ? (double)p[u].z : 0.0};
 #pragma unroll
-      for (int u = 0; u < CEN_U; u++) {
-        const double x = v[a][u], ax = fabs(x);
-        L += x;
-        AB = __dadd_ru(AB, ax);  // rounded up: M below is a true upper bound
-        mn = (ax != 0.0 && ax < mn) ? ax : mn;
+      for (int a = 0; a < 3; a++) {
+        const double ax = fabs(v[a]);
+        L[a] += v[a];
+        AB[a] = __dadd_ru(AB[a], ax);  // rounded up: a true upper bound
+        mn[a] = (ax != 0.0 && ax < mn[a]) ? ax : mn[a];
       }
+    }
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        L += __shfl_xor_sync(FULL, L, off);
-        AB = __dadd_ru(AB, __shfl_xor_sync(FULL, AB, off));
-        const double o = __shfl_xor_sync(FULL, mn, off);
-        mn = o < mn ? o : mn;
-      }
-      const double M = __dadd_ru(fabs(S[a]), AB);  // >= |any partial sum| of the walk through this chunk
-      bool exact = M < 1e300;                      // finite
-      if (exact && AB != 0.0) {
-        int q = dexp(mn) - 23;  // float ulp of the smallest non-zero addend
-        const int qs = lowbit_exp(S[a]);
-        q = qs < q ? qs : q;
-        exact = dexp(M) - q <= 52;  // M < 2^(q+53): every multiple of 2^q up to M is a double
-      }
-      if (exact) {
-        S[a] += L;  // = the sequential result (no rounding anywhere)
-      } else {      // walk the chunk in point order: i = base + u*32 + lane
-        double s = S[a];
+    for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
-        for (int u = 0; u < CEN_U; u++) {
-          const unsigned um = __ballot_sync(FULL, (use >> u) & 1u);
-          for (int l = 0; l < 32; l++) {
-            const double x = __shfl_sync(FULL, v[a][u], l);
-            if ((um >> l) & 1u) s += x;
-          }
+      for (int a = 0; a < 3; a++) {
+        L[a] += __shfl_xor_sync(FULL, L[a], off);
+        AB[a] = __dadd_ru(AB[a], __shfl_xor_sync(FULL, AB[a], off));
+        const double o = __shfl_xor_sync(FULL, mn[a], off);
+        mn[a] = o < mn[a] ? o : mn[a];
+      }
+    }
+    used = __reduce_add_sync(FULL, used);
+    if (lane == 0) {
+      double *r = recs + (rec_off[blockIdx.y] + ch) * CEN_REC;
+#pragma unroll
+      for (int a = 0; a < 3; a++) r[a * 3] = L[a], r[a * 3 + 1] = AB[a], r[a * 3 + 2] = mn[a];
+      r[9] = (double)used;
+    }
+  }
+}
+
+// (2) one warp per map walks its chunk records in order (lanes prefetch 32 records at a time, the recurrence on S is a
+// few dozen instructions per chunk); a chunk that fails the exactness test is walked point by point.
+__global__ void __launch_bounds__(32) k_centroid(const BuildJob *__restrict__ jobs, const int *__restrict__ which,
+                                                 const long long *__restrict__ rec_off, const double *__restrict__ recs,
+                                                 double *__restrict__ out) {
+  const BuildJob &j = jobs[which[blockIdx.x]];
+  const int lane = threadIdx.x;
+  const int nchunks = (j.npts + CEN_CHUNK - 1) / CEN_CHUNK;
+  const double *rbase = recs + rec_off[blockIdx.x] * CEN_REC;
+  double S[3] = {0.0, 0.0, 0.0};
+  long long cnt = 0;
+  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+    double r[CEN_REC];
+#pragma unroll
+    for (int q = 0; q < CEN_REC; q++) r[q] = (c0 + lane < nchunks) ? rbase[(size_t)(c0 + lane) * CEN_REC + q] : 0.0;
+    const int m = min(32, nchunks - c0);
+    for (int l = 0; l < m; l++) {
+      cnt += (long long)__shfl_sync(FULL, r[9], l);
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const double L = __shfl_sync(FULL, r[a * 3], l), AB = __shfl_sync(FULL, r[a * 3 + 1], l), mn = __shfl_sync(FULL, r[a * 3 + 2], l);
+        const double M = __dadd_ru(fabs(S[a]), AB);  // >= |any partial sum| of the walk through this chunk
+        bool exact = M < 1e300;
+        if (exact && AB != 0.0) {
+          int q = dexp(mn) - 23;  // float ulp of the smallest non-zero addend
+          const int qs = lowbit_exp(S[a]);
+          q = qs < q ? qs : q;
+          exact = dexp(M) - q <= 52;  // M < 2^(q+53): every multiple of 2^q up to M is a double
         }
-        S[a] = s;
+        if (exact) {
+          S[a] += L;  // = the sequential result (no rounding anywhere)
+        } else {      // walk the chunk in point order
+          const int base = (c0 + l) * CEN_CHUNK;
+          double s = S[a];
+          for (int u = 0; u < CEN_U; u++) {
+            const int i = base + u * 32 + lane;
+            float4 p = make_float4(nanf(""), 0.f, 0.f, 0.f);
+            if (i < j.npts) p = j.pts[i];
+            const bool ok = !pt_skip(p, j.range_limit);
+            const double x = a == 0 ? (double)p.x : (a == 1 ? (double)p.y : (double)p.z);
+            const unsigned um = __ballot_sync(FULL, ok);
+            for (int ll = 0; ll < 32; ll++) {
+              const double xx = __shfl_sync(FULL, x, ll);
+              if ((um >> ll) & 1u) s += xx;
+            }
+          }
+          S[a] = s;
+        }
       }
     }
   }
@@ -168,7 +211,9 @@ __global__ void k_mark(const BuildJob *__restrict__ jobs) {
         in_grid(j.g, ix, iy, iz)) {
       const int b = block_id(j.g, ix, iy, iz), bit = block_bit(ix, iy, iz);
       key = b * 64 + bit;
-      atomicOr(j.amask + b, 1ull << bit);
+      // ~90 % of the points fall into a voxel that is already marked: look before taking the (contended) atomic.  A stale
+      // read only costs a redundant atomicOr.
+      if (!((__ldcg(j.amask + b) >> bit) & 1ull)) atomicOr(j.amask + b, 1ull << bit);
     }
     j.pt_cell[i] = key;
   }
@@ -226,7 +271,7 @@ __global__ void k_count(const BuildJob *__restrict__ jobs) {
     const int b = key >> 6, bit = key & 63;
     const int c = j.abase[b] + __popcll(j.amask[b] & ((1ull << bit) - 1ull));
     j.pt_cell[i] = c;
-    atomicAdd(j.cnt + c, 1);
+    j.seg2[i] = atomicAdd(j.cnt + c, 1);  // arrival rank inside the cell (arbitrary order; k_sort_segments orders the ids)
   }
 }
 
@@ -250,7 +295,7 @@ __global__ void k_scatter(const BuildJob *__restrict__ jobs) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
     const int c = j.pt_cell[i];
     if (c < 0) continue;
-    j.seg_idx[j.seg_off[c] + atomicAdd(j.cursor + c, 1)] = i;
+    j.seg_idx[j.seg_off[c] + j.seg2[i]] = i;  // the rank k_count drew: no second round of atomics
   }
 }
 
@@ -711,10 +756,15 @@ static inline int chunks_for(int n, int per) {
   return c < 1 ? 1 : (c > 1024 ? 1024 : c);
 }
 
-int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, double *d_out, cudaStream_t s) {
-  k_centroid<<<n_which, 32, 0, s>>>(d_jobs, d_which, d_out);
+int centroid_chunk_points() { return CEN_CHUNK; }
+int centroid_record_doubles() { return CEN_REC; }
+int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, const long long *d_rec_off, double *d_recs,
+                 double *d_out, cudaStream_t s) {
+  const int max_chunks = (max_pts + CEN_CHUNK - 1) / CEN_CHUNK;
+  k_centroid_chunks<<<dim3(chunks_for(max_chunks, 4), n_which), 128, 0, s>>>(d_jobs, d_which, d_rec_off, d_recs);
+  k_centroid<<<n_which, 32, 0, s>>>(d_jobs, d_which, d_rec_off, d_recs, d_out);
   k_extent<<<dim3(chunks_for(max_pts, 1024), n_which), 256, 0, s>>>(d_jobs, d_which, d_out);
-  return 2;
+  return 3;
 }
 int launch_mark(const BuildJob *d_jobs, int n, int max_pts, cudaStream_t s) {
   k_mark<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);

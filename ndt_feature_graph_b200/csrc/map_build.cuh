@@ -48,7 +48,12 @@ struct BuildJob {
   double log_occ;  // log(0.6/0.4) evaluated on the host
 };
 
-int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, double *d_out, cudaStream_t s);
+int centroid_chunk_points();
+int centroid_record_doubles();
+// d_rec_off[w] = first chunk record of map w in d_recs (records of centroid_record_doubles() doubles, one per
+// centroid_chunk_points() points)
+int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, const long long *d_rec_off, double *d_recs,
+                 double *d_out, cudaStream_t s);
 int launch_mark(const BuildJob *d_jobs, int n, int max_pts, cudaStream_t s);
 int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int max_cells, cudaStream_t s);
 int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s);

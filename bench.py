@@ -181,8 +181,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.pairs
-    # every rank owns B distinct pairs (weak scaling: per-GPU work fixed); seed = rank
-    tg, sr, T0s, Ds = synth.velodyne_batch(B, n_base=args.base, seed=rank)
+    # every rank owns B distinct pairs of one workload (weak scaling: per-GPU work fixed): pairs [rank*B, (rank+1)*B)
+    tg, sr, T0s, Ds = synth.velodyne_batch(B, n_base=args.base, seed=0, start=rank * B)
     stream = torch.cuda.Stream(dev)
     eng = N.Engine(local, stream=stream.cuda_stream)
     prm = eng.default_params()
@@ -201,7 +201,7 @@ def run_gpu(args):
     def step_device():
         eng.register_scans_raw(B, tp, tn, sp, sn, T0c.ctypes.data, CELL, -1.0, prm, True, api.DEVICE, api.DEVICE,
                                d_res.data_ptr(), d_cov.data_ptr())
-        if world > 1:  # the only cross-GPU step: gather of the per-edge result records (NCCL over NVLink)
+        if world > 1 and not os.environ.get("NDTB_BENCH_NO_GATHER"):  # the only cross-GPU step: gather of the result records (NCCL)
             with torch.cuda.stream(stream):
                 sharding.gather_results(d_res, world * B, rank, world)
 

@@ -63,6 +63,22 @@ struct ndtb_ctx {
     }                                                                                               \
   } while (0)
 
+// CUDA's current device is per host thread: a context created on device 1 and then driven from a fresh thread (whose
+// current device is 0) would create its events and slabs on the wrong device.  Every entry point that touches CUDA
+// therefore switches to the context's device and restores the caller's on return.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const ndtb_ctx *ctx) {
+    if (!ctx) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != ctx->device) cudaSetDevice(ctx->device);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 namespace {
 
 // NDTB_PROFILE=1: host-side phase timer (synchronises the stream at every mark; debugging aid, never on in benchmarks)
@@ -566,7 +582,11 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
         }
         CU_TRY(ctx, cudaEventRecord(ctx->aux_ev[0], st));  // first launch complete
       }
-      const int G2 = pow2_floor(std::min(8, std::max(1, sms / n_unf)));
+      // Always the widest cluster, even when n_unf x 8 exceeds the SMs: most of the handed-over registrations need only
+      // a few more passes and leave quickly; the wall time is set by the few that need hundreds of passes, i.e. by the
+      // latency of one pass (measured: 62 ms vs 72 ms for 592 pairs with 30 hand-overs).
+      int G2 = 8;
+      if (const char *g2 = std::getenv("NDTB_G2")) G2 = pow2_floor(std::max(1, std::min(8, std::atoi(g2))));  // A/B knob
       CU_TRY(ctx, launch_match(d_jobs, d_unf + 1, n_unf, G2, cfg, d_res, s->p + o_states, 1, 0, d_unf, nullptr, st));
       ctx->launches += 1;
       if (do_cov) {
@@ -654,6 +674,7 @@ int ndtb_ctx_create(int device, void *stream, ndtb_ctx **out) {
 }
 
 void ndtb_ctx_destroy(ndtb_ctx *ctx) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx) return;
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream), cudaStreamDestroy(ctx->copy_stream);
@@ -666,6 +687,7 @@ void ndtb_ctx_destroy(ndtb_ctx *ctx) {
 }
 
 int ndtb_ctx_synchronize(ndtb_ctx *ctx) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx) return NDTB_ERR_ARG;
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return NDTB_OK;
@@ -677,6 +699,7 @@ int ndtb_ctx_enable_timing(ndtb_ctx *ctx, int on) {
   return NDTB_OK;
 }
 int ndtb_ctx_match_time(ndtb_ctx *ctx, double *ms, int64_t *launches) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !ms) return NDTB_ERR_ARG;
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   double tot = 0;
@@ -717,7 +740,10 @@ int ndtb_map_create(ndtb_ctx *ctx, double cx, double cy, double cz, ndtb_map **o
   *out = m;
   return NDTB_OK;
 }
-void ndtb_map_destroy(ndtb_map *m) { delete m; }
+void ndtb_map_destroy(ndtb_map *m) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
+  delete m;
+}
 
 int ndtb_map_guess_size(ndtb_map *m, double cx, double cy, double cz, double sx, double sy, double sz) {
   if (!m) return NDTB_ERR_ARG;
@@ -743,6 +769,7 @@ int ndtb_map_initialize(ndtb_map *m, double cx, double cy, double cz, double sx,
 }
 
 int ndtb_map_load_point_cloud(ndtb_map *m, const float *pts, int64_t n, double range_limit, int mem, int64_t *n_binned) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
   if (!m || n < 0 || n > 0x7fffffff || (n > 0 && !pts)) return NDTB_ERR_ARG;
   ndtb_ctx *ctx = m->ctx;
   SlabP buf;
@@ -768,6 +795,7 @@ int ndtb_map_load_point_cloud(ndtb_map *m, const float *pts, int64_t n, double r
 }
 
 int ndtb_map_add_points(ndtb_map *m, const float *pts, int64_t n, int mem, int64_t *n_binned) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
   if (!m || n < 0 || n > 0x7fffffff || (n > 0 && !pts)) return NDTB_ERR_ARG;
   if (!m->grid_ready) return NDTB_ERR_GRID;
   ndtb_ctx *ctx = m->ctx;
@@ -790,6 +818,7 @@ int ndtb_map_add_points(ndtb_map *m, const float *pts, int64_t n, int mem, int64
 }
 
 int ndtb_map_compute_cells(ndtb_map *m, uint32_t maxnumpoints, float occupancy_limit) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
   if (!m) return NDTB_ERR_ARG;
   ndtb_ctx *ctx = m->ctx;
   if (m->pending.empty()) return NDTB_OK;
@@ -827,6 +856,7 @@ int ndtb_map_compute_cells(ndtb_map *m, uint32_t maxnumpoints, float occupancy_l
 
 int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, const float *const *pts, const int64_t *n_pts,
                          double range_limit, int mem, uint32_t maxnumpoints, float occupancy_limit) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || n_maps < 0 || (n_maps > 0 && (!maps || !pts || !n_pts))) return NDTB_ERR_ARG;
   std::vector<ndtb_map *> mv((size_t)n_maps);
   std::vector<PointSrc> ps((size_t)n_maps);
@@ -900,6 +930,7 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
 }
 
 int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells, int64_t n, int use_idx) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
   if (!m || !g || n < 0 || (n > 0 && !cells)) return NDTB_ERR_ARG;
   ndtb_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
@@ -981,6 +1012,7 @@ int64_t ndtb_map_num_cells(const ndtb_map *m, int gaussian_only) {
 }
 
 int64_t ndtb_map_export_cells(const ndtb_map *m, ndtb_cell *out, int64_t cap, int gaussian_only) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
   if (!m || cap < 0 || (cap > 0 && !out)) return NDTB_ERR_ARG;
   ndtb_ctx *ctx = m->ctx;
   if (m->n_all == 0) return 0;
@@ -1007,6 +1039,7 @@ int64_t ndtb_map_export_cells(const ndtb_map *m, ndtb_cell *out, int64_t cap, in
 }
 
 int64_t ndtb_map_point_indices(const ndtb_map *m, const float *pts, int64_t n, int mem, int32_t *out) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
   const bool count_only = mem == NDTB_MEM_DEVICE + 1;  // internal: device points, no index output
   if (count_only) mem = NDTB_MEM_DEVICE;
   if (!m || n < 0 || n > 0x7fffffff || (n > 0 && (!pts || (!out && !count_only)))) return NDTB_ERR_ARG;
@@ -1034,6 +1067,7 @@ int64_t ndtb_map_point_indices(const ndtb_map *m, const float *pts, int64_t n, i
 // ---- matcher
 int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T, const ndtb_params *p,
                          int want_hessian, double *out43, int64_t *n_pairs) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !tgt || !src || !T || !p || !out43) return NDTB_ERR_ARG;
   if (!map_ok(tgt) || !map_ok(src)) return NDTB_ERR_GRID;
   if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(tgt))) return rc;
@@ -1064,12 +1098,14 @@ int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src
 
 int ndtb_d2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0, const ndtb_params *p,
                    ndtb_result *res) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !tgt || !src || !T0 || !p || !res) return NDTB_ERR_ARG;
   return match_batch_impl(ctx, 1, &tgt, &src, T0, nullptr, p, 0, NDTB_MEM_HOST, res, nullptr);
 }
 
 int ndtb_fusion_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0, const double *Tcov36,
                       const ndtb_params *p, ndtb_result *res) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !tgt || !src || !T0 || !Tcov36 || !p || !res) return NDTB_ERR_ARG;
   double Q[36];
   if (!inv6(Tcov36, Q)) return NDTB_ERR_SINGULAR;
@@ -1079,12 +1115,14 @@ int ndtb_fusion_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, c
 int ndtb_d2d_match_batch(ndtb_ctx *ctx, int64_t n_edges, const ndtb_map *const *tgt, const ndtb_map *const *src,
                          const double *T0s, const ndtb_params *p, int with_covariance, int out_mem, ndtb_result *res,
                          double *cov36s) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || n_edges < 0 || (n_edges > 0 && (!tgt || !src || !T0s || !res)) || !p) return NDTB_ERR_ARG;
   return match_batch_impl(ctx, n_edges, tgt, src, T0s, nullptr, p, with_covariance && cov36s, out_mem, res, cov36s);
 }
 
 int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T, const ndtb_params *p,
                         double *cov36) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !tgt || !src || !T || !p || !cov36) return NDTB_ERR_ARG;
   if (!map_ok(tgt) || !map_ok(src)) return NDTB_ERR_GRID;
   if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(tgt))) return rc;
@@ -1140,6 +1178,7 @@ int points_source(ndtb_ctx *ctx, const float *pts, int64_t n, int mem, std::uniq
 
 int ndtb_p2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const float *pts, int64_t n, int mem, const double *T,
                          const ndtb_params *p, int want_hessian, double *out43, int64_t *n_pairs) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !tgt || !T || !p || !out43) return NDTB_ERR_ARG;
   std::unique_ptr<ndtb_map> src;
   if (int rc = points_source(ctx, pts, n, mem, src)) return rc;
@@ -1148,6 +1187,7 @@ int ndtb_p2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const float *pts, i
 
 int ndtb_p2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const float *pts, int64_t n, int mem, const double *T0,
                    const ndtb_params *p, ndtb_result *res) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !tgt || !T0 || !p || !res) return NDTB_ERR_ARG;
   std::unique_ptr<ndtb_map> src;
   if (int rc = points_source(ctx, pts, n, mem, src)) return rc;
@@ -1159,6 +1199,7 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
                         const float *const *src_pts, const int64_t *n_src, const double *T0s, double cell,
                         const double *map_size, double range_limit, const ndtb_params *p, int with_covariance, int in_mem,
                         int out_mem, ndtb_result *res, double *cov36s) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || n_pairs < 0 || !p || !(cell > 0)) return NDTB_ERR_ARG;
   if (n_pairs == 0) return NDTB_OK;
   if (!tgt_pts || !n_tgt || !src_pts || !n_src || !T0s || !res) return NDTB_ERR_ARG;
@@ -1199,6 +1240,7 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
 }
 
 int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T, double *score) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !ref || !mov || !T || !score) return NDTB_ERR_ARG;
   if (!map_ok(ref) || !map_ok(mov)) return NDTB_ERR_GRID;
   if (mov->n_all == 0 || ref->n_all == 0) {

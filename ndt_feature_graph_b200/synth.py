@@ -226,18 +226,19 @@ def _apply(G, cloud):
     return out
 
 
-def velodyne_batch(n_pairs, n_base=8, seed=0, n_rings=64, n_az=1563):
-    """n_pairs scan pairs of config C2.  n_base scenes are ray-cast (slow, numpy); every pair is a base pair moved by
-    its own rigid transform G (both scans), which changes the voxelisation of both maps, so all pairs are distinct
-    data.  Returns lists (target clouds, source clouds, initial guesses T0, true transforms D)."""
-    base = [velodyne_pair(100 * seed + b, n_rings, n_az) for b in range(min(n_base, n_pairs))]
-    rng = np.random.default_rng(9000 + seed)
+def velodyne_batch(n_pairs, n_base=8, seed=0, n_rings=64, n_az=1563, start=0):
+    """Pairs [start, start + n_pairs) of the C2 workload `seed`.  n_base scenes are ray-cast (slow, numpy); pair i is base
+    pair i % n_base moved by its own rigid transform G_i (both scans), which changes the voxelisation of both maps, so
+    all pairs are distinct data.  G_i and the initial guess depend only on (seed, i): ranks of a multi-GPU run take
+    disjoint index ranges of ONE workload.  Returns lists (target clouds, source clouds, initial guesses T0, true D)."""
+    base = [velodyne_pair(100 * seed + b, n_rings, n_az) for b in range(min(n_base, start + n_pairs))]
     tg, sr, T0s, Ds = [], [], [], []
-    for i in range(n_pairs):
+    for i in range(start, start + n_pairs):
         ca, cb, D = base[i % len(base)]
         if i < len(base):
             G = np.eye(4)
         else:
+            rng = np.random.default_rng([9000 + seed, i])
             G = pose_from_xyzrpy(rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(-0.2, 0.2), 0.0, 0.0, rng.uniform(-np.pi, np.pi))
         Gi = np.linalg.inv(G)
         Di = G @ D @ Gi

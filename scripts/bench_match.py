@@ -14,7 +14,7 @@ from ndt_feature_graph_b200 import synth  # noqa: E402
 
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-cache = f"/tmp/ndtb_workload_{pairs}.pkl"
+cache = f"/tmp/ndtb_workload_v2_{pairs}.pkl"
 if os.path.exists(cache):
     tg, sr, T0s, Ds = pickle.load(open(cache, "rb"))
 else:

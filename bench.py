@@ -183,8 +183,13 @@ def run_gpu(args):
     B = args.pairs
     # every rank owns B distinct pairs of one workload (weak scaling: per-GPU work fixed): pairs [rank*B, (rank+1)*B)
     tg, sr, T0s, Ds = synth.velodyne_batch(B, n_base=args.base, seed=0, start=rank * B)
-    stream = torch.cuda.Stream(dev)
-    eng = N.Engine(local, stream=stream.cuda_stream)
+    # `lanes` contexts (one host thread + one stream each, the ABI's "one ndtb_ctx per host thread") take the steps in turn:
+    # while one step's last registrations (the few that need hundreds of passes) finish on a few SMs, the next step's
+    # kernels fill the rest of the GPU.  Every step does the full work on the same B pairs.
+    lanes = max(1, args.lanes)
+    streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
+    engs_d = [N.Engine(local, stream=st.cuda_stream) for st in streams]
+    stream, eng = streams[0], engs_d[0]
     prm = eng.default_params()
     # device-resident scans
     d_t = [torch.from_numpy(c).to(dev) for c in tg]
@@ -194,48 +199,103 @@ def run_gpu(args):
     tn = (C.c_int64 * B)(*[c.shape[0] for c in tg])
     sn = (C.c_int64 * B)(*[c.shape[0] for c in sr])
     T0c = np.concatenate([np.ascontiguousarray(T.T).ravel() for T in T0s])
-    d_res = torch.zeros(B * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    d_cov = torch.zeros(B * 36, dtype=torch.float64, device=dev)
+    d_ress = [torch.zeros(B * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev) for _ in range(lanes)]
+    d_covs = [torch.zeros(B * 36, dtype=torch.float64, device=dev) for _ in range(lanes)]
+    d_res, d_cov = d_ress[0], d_covs[0]
     in_bytes = 16 * (sum(c.shape[0] for c in tg) + sum(c.shape[0] for c in sr))
 
-    def step_device():
-        eng.register_scans_raw(B, tp, tn, sp, sn, T0c.ctypes.data, CELL, -1.0, prm, True, api.DEVICE, api.DEVICE,
-                               d_res.data_ptr(), d_cov.data_ptr())
-        if world > 1 and not os.environ.get("NDTB_BENCH_NO_GATHER"):  # the only cross-GPU step: gather of the result records (NCCL)
-            with torch.cuda.stream(stream):
-                sharding.gather_results(d_res, world * B, rank, world)
+    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+
+    def step_device(k=0):
+        engs_d[k].register_scans_raw(B, tp, tn, sp, sn, T0c.ctypes.data, CELL, -1.0, prm, True, api.DEVICE, api.DEVICE,
+                                     d_ress[k].data_ptr(), d_covs[k].data_ptr())
+
+    def gather_step(records, ev):
+        # the only cross-GPU step: gather of the per-edge result records (NCCL over NVLink), always issued by the main
+        # thread in step order (collectives of one process group must be issued in the same order on every rank)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ev)
+            sharding.gather_results(records, world * B, rank, world)
+
+    def run_device_steps(n_steps):
+        import threading
+
+        do_gather = world > 1 and not os.environ.get("NDTB_BENCH_NO_GATHER")
+        snaps, evs = [None] * n_steps, [torch.cuda.Event() for _ in range(n_steps)]
+        done = [threading.Event() for _ in range(n_steps)]
+
+        def worker(k):
+            torch.cuda.set_device(local)
+            for s_ in range(k, n_steps, lanes):
+                step_device(k)
+                if do_gather:
+                    with torch.cuda.stream(streams[k]):
+                        snaps[s_] = d_ress[k].clone()  # lane k's next step overwrites its record buffer
+                        evs[s_].record(streams[k])
+                done[s_].set()
+
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(lanes)]
+        for t_ in th:
+            t_.start()
+        for s_ in range(n_steps):
+            done[s_].wait()
+            if do_gather:
+                gather_step(snaps[s_], evs[s_])
+        for t_ in th:
+            t_.join()
 
     def sync_all():
-        stream.synchronize()
+        for st in streams:
+            st.synchronize()
+        if comm_stream is not None:
+            comm_stream.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    for _ in range(args.warmup):
-        step_device()
+    run_device_steps(max(args.warmup, lanes))
     sync_all()
-    eng.enable_timing(True)
-    eng.match_time()
-    l0 = eng.launch_count
+    l0 = sum(e.launch_count for e in engs_d)
     clk = ClockSampler(local)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1s = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
     sync_all()
     ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    ev1.record(stream)
+    for st in streams[1:]:
+        st.wait_event(ev0)
+    run_device_steps(args.steps)
+    for k in range(lanes):
+        ev1s[k].record(streams[k])
+    if comm_stream is not None:
+        ev1s.append(torch.cuda.Event(enable_timing=True))
+        ev1s[-1].record(comm_stream)
     sync_all()
-    ms = ev0.elapsed_time(ev1)
+    ms = max(ev0.elapsed_time(e) for e in ev1s)
     clocks = clk.stop()
-    launches = eng.launch_count - l0
+    launches = sum(e.launch_count for e in engs_d) - l0
+    # roofline of the dominant kernel: its launches timed alone (one lane), CUDA events inside the library
+    eng.enable_timing(True)
+    eng.match_time()
+    for _ in range(max(2, min(args.steps, 3))):
+        step_device(0)
     match_ms, match_n = eng.match_time()
     eng.enable_timing(False)
+    sync_all()
+    solo0, solo1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    solo0.record(stream)
+    step_device(0)
+    solo1.record(stream)
+    sync_all()
+    solo_ms = solo0.elapsed_time(solo1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=api.RESULT_DTYPE)
     cov = d_cov.cpu().numpy().reshape(B, 6, 6)
+    for k in range(1, lanes):
+        if True:
+            assert np.array_equal(np.frombuffer(d_ress[k].cpu().numpy().tobytes(), dtype=api.RESULT_DTYPE)["T"], res["T"]), "lanes disagree"
 
     # ---- e2e: host (pinned) scans -> C ABI -> host results, copies inside the timed region
     h_t = [torch.from_numpy(c).pin_memory() for c in tg]
@@ -249,6 +309,7 @@ def run_gpu(args):
     # ABI's "one ndtb_ctx per host thread"), consecutive steps alternate between them, so the H2D upload of step s+1
     # overlaps the registration kernels of step s.  Every step still uploads its own scans and reads back its own
     # results; the timed region is the wall time until the last step's results are in host memory.
+    lanes_d = lanes
     lanes = max(1, args.e2e_lanes)
     engs = [eng] + [N.Engine(local) for _ in range(lanes - 1)]
     h_ress = [np.zeros(B, api.RESULT_DTYPE) for _ in range(lanes)]
@@ -306,7 +367,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "base_scenes": args.base,
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "base_scenes": args.base, "lanes": lanes_d,
                        "points_per_scan": int(np.mean([c.shape[0] for c in tg])),
                        "gaussian_cells_per_map": int(res["n_tgt_cells"].mean()),
                        "n_neighbours": int(prm.n_neighbours), "delta_score": prm.delta_score,
@@ -321,7 +382,7 @@ def run_gpu(args):
             "roofline": {"kernel": "match_kernel (device-resident Newton loop around the D2D derivative pass)",
                          "bound": "hbm", "achieved": alg_bytes_launch / t_launch / 1e9, "peak": hbm, "unit": "GB/s",
                          "frac": alg_bytes_launch / t_launch / 1e9 / hbm, "peak_source": hbm_src, "traffic": None,
-                         "launch_ms": 1e3 * t_launch, "share_of_step": match_ms / ms,
+                         "launch_ms": 1e3 * t_launch, "share_of_step": 1e3 * t_launch / solo_ms, "step_ms_one_lane": solo_ms,
                          "note": "working set is L1/L2 resident; the binding limit is fp64 CUDA-core throughput, see DESIGN.md"},
         }
         if world == 1 and not args.no_cpu:
@@ -360,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) leg: profiling runs only")
+    ap.add_argument("--lanes", type=int, default=1, help="contexts (host thread + stream each) the device-resident leg alternates its steps between")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="contexts (host threads) the e2e leg alternates its steps between")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the step timed on the CPU (0 = auto, ~10-30 s)")
     args = ap.parse_args()

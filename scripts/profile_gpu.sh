@@ -1,16 +1,24 @@
 #!/bin/bash
-# Runs on the GPU box (under gpurun): launch list + full ncu captures of one bench step.  Outputs -> gpurun_out/
+# Runs on the GPU box (under gpurun): launch list + ncu captures of one bench step.  Outputs -> gpurun_out/ (CSV exports;
+# only the match-kernel report itself is kept, gpurun brings back at most 64 MiB).
 # usage: scripts/profile_gpu.sh <tag> [pairs]
 set -u
 TAG=${1:-r01}
-PAIRS=${2:-296}
+PAIRS=${2:-592}
 OUT=gpurun_out
 mkdir -p $OUT
 BENCH="python bench.py --steps 1 --warmup 1 --pairs $PAIRS --no-cpu --no-e2e"
 # 1) every launch of warm-up + timed step with its device time
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $BENCH > $OUT/launches_$TAG.log 2>&1
-# 2) full capture of the registration kernel (timed step = 2nd and later launches)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:match_kernel -s 1 -c 2 -f -o $OUT/match_$TAG $BENCH > $OUT/match_$TAG.log 2>&1
-# 3) full capture of the map-build + covariance kernels of the timed step
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^k_|cov_' -s 13 -c 13 -f -o $OUT/build_$TAG $BENCH > $OUT/build_$TAG.log 2>&1
+# 2) full capture of the registration kernel: first (1 CTA per registration) and finishing (8-CTA clusters) launch of a step
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:match_kernel -s 2 -c 2 -f -o $OUT/match_$TAG $BENCH > $OUT/match_$TAG.log 2>&1
+ncu -i $OUT/match_$TAG.ncu-rep --page raw --csv > $OUT/match_${TAG}_raw.csv 2>/dev/null
+ncu -i $OUT/match_$TAG.ncu-rep --page source --csv > $OUT/match_${TAG}_source.csv 2>/dev/null
+# 3) lighter capture of the map-build + covariance kernels of one step
+timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy --section WarpStateStats \
+  --clock-control none -k regex:'k_|cov_' -s 20 -c 20 -f -o $OUT/build_$TAG $BENCH > $OUT/build_$TAG.log 2>&1
+ncu -i $OUT/build_$TAG.ncu-rep --page raw --csv > $OUT/build_${TAG}_raw.csv 2>/dev/null
+rm -f $OUT/build_$TAG.ncu-rep
+gzip -f $OUT/match_${TAG}_source.csv
 ls -la $OUT
+du -sh $OUT

@@ -203,6 +203,16 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
                         const double *map_size, double range_limit, const ndtb_params *p,
                         int with_covariance, int in_mem, int out_mem, ndtb_result *res, double *cov36s);
 
+/* ---- JFF map files: NDTMap::writeToJFF / loadFromJFF [upstream]; call sites ndt_feature_fuser_hmt.cpp:15,24,39 ----
+ * Host-side format code (no GPU needed): the grid + the cells that carry information (hasGaussian_, N > 0 or a
+ * non-zero occupancy), ndtb_cell.idx = voxel index.  Byte layout in csrc/jff.cpp, decoded from the maps the reference
+ * ships.  ndtb_jff_read_cells with cells == NULL returns the count in *n. */
+int ndtb_jff_write_cells(const char *path, const ndtb_grid *g, const ndtb_cell *cells, int64_t n);
+int ndtb_jff_read_cells(const char *path, ndtb_grid *g, ndtb_cell *cells, int64_t cap, int64_t *n);
+/* the same for a map resident in HBM (export + write / read + ndtb_map_from_cells); 0 on success like upstream */
+int ndtb_map_write_jff(const ndtb_map *m, const char *path);
+int ndtb_map_load_jff(ndtb_map *m, const char *path);
+
 /* ndt_feature::overlapNDTOccupancyScore(ref, mov, T) */
 int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T,
                        double *score);

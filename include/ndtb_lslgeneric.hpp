@@ -8,6 +8,7 @@
 //   lslgeneric::NDTMap(SpatialIndex*, bool dealloc=false)                  ndt_feature_fuser_hmt.cpp:87,196
 //     initialize / guessSize / setMapSize / loadPointCloud / addPointCloud / computeNDTCells
 //                                                                         ndt_feature_fuser_hmt.cpp:89-94,201-227,485-486
+//     writeToJFF / loadFromJFF                                            ndt_feature_fuser_hmt.cpp:15,24,39
 //     numberOfActiveCells / getAllCells / getAllInitializedCells / pseudoTransformNDT / getCentroid
 //                                                                         ndt_matcher_d2d_fusion.h:840, ndt_feature_node.h:216
 //   lslgeneric::NDTCell {getMean,getCov,setMean,setCov,getCenter,getOccupancy,hasGaussian_}
@@ -299,6 +300,9 @@ class NDTMap {
                               ? ndtb_map_compute_cells(h_, maxnumpoints, occupancy_limit)
                               : NDTB_ERR_ARG;  // other update modes are not reachable from the reference
   }
+  // writeToJFF / loadFromJFF (ndt_feature_fuser_hmt.cpp:15,24,39): 0 on success, like upstream
+  int writeToJFF(const char *filename) { return h_ ? ndtb_map_write_jff(h_, filename) : NDTB_ERR_CUDA; }
+  int loadFromJFF(const char *filename) { return h_ ? ndtb_map_load_jff(h_, filename) : NDTB_ERR_CUDA; }
   int numberOfActiveCells() const { return h_ ? (int)ndtb_map_num_cells(h_, 1) : 0; }
   bool getGridSizeInMeters(double &cx, double &cy, double &cz) const {
     ndtb_grid g;

@@ -134,6 +134,10 @@ def load_library():
         "ndtb_p2d_match": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, PP, PR]),
         "ndtb_d2d_match_batch": (C.c_int, [vp, i64, vp, vp, vp, PP, C.c_int, C.c_int, vp, vp]),
         "ndtb_register_scans": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, dbl, vp, dbl, PP, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "ndtb_jff_write_cells": (C.c_int, [C.c_char_p, C.POINTER(Grid), vp, i64]),
+        "ndtb_jff_read_cells": (C.c_int, [C.c_char_p, C.POINTER(Grid), vp, i64, C.POINTER(i64)]),
+        "ndtb_map_write_jff": (C.c_int, [vp, C.c_char_p]),
+        "ndtb_map_load_jff": (C.c_int, [vp, C.c_char_p]),
         "ndtb_overlap_score": (C.c_int, [vp, vp, vp, vp, C.POINTER(dbl)]),
     }
     for name, (res, args) in sig.items():
@@ -159,6 +163,31 @@ def _pts4(pts):
     if pts.shape[1] == 3:
         pts = np.concatenate([pts, np.zeros((pts.shape[0], 1), np.float32)], axis=1)
     return np.ascontiguousarray(pts)
+
+
+def jff_write_cells(path, center, cell, size, cells):
+    """NDTMap::writeToJFF format from host arrays (no GPU): cells = structured array CELL_DTYPE with voxel indices."""
+    L = load_library()
+    g = Grid((C.c_double * 3)(*center), (C.c_double * 3)(*cell), (C.c_int32 * 3)(*[int(s) for s in size]))
+    cells = np.ascontiguousarray(cells, dtype=CELL_DTYPE)
+    rc = L.ndtb_jff_write_cells(str(path).encode(), C.byref(g), cells.ctypes.data, cells.shape[0])
+    if rc != 0:
+        raise NdtbError(f"jff write failed: {L.ndtb_strerror(rc).decode()}")
+
+
+def jff_read_cells(path):
+    """NDTMap::loadFromJFF format into host arrays (no GPU): returns (center, cell, size, cells)."""
+    L = load_library()
+    g = Grid()
+    n = C.c_int64(0)
+    rc = L.ndtb_jff_read_cells(str(path).encode(), C.byref(g), None, 0, C.byref(n))
+    if rc != 0:
+        raise NdtbError(f"jff read failed: {L.ndtb_strerror(rc).decode()}")
+    cells = np.zeros(max(n.value, 1), CELL_DTYPE)
+    rc = L.ndtb_jff_read_cells(str(path).encode(), C.byref(g), cells.ctypes.data, n.value, C.byref(n))
+    if rc != 0:
+        raise NdtbError(f"jff read failed: {L.ndtb_strerror(rc).decode()}")
+    return np.array(g.center), np.array(g.cell), np.array(g.size), cells[: n.value].copy()
 
 
 class Engine:
@@ -350,6 +379,14 @@ class NDTMap:
         if k < 0:
             self.e.check(int(k))
         return out, int(k)
+
+    def writeToJFF(self, path):
+        """NDTMap::writeToJFF (ndt_feature_fuser_hmt.cpp:15): 0 on success."""
+        return int(self.e.L.ndtb_map_write_jff(self.h, str(path).encode()))
+
+    def loadFromJFF(self, path):
+        """NDTMap::loadFromJFF (ndt_feature_fuser_hmt.cpp:24,39): 0 on success."""
+        return int(self.e.L.ndtb_map_load_jff(self.h, str(path).encode()))
 
     def overlapNDTOccupancyScore(self, mov, T):
         """ndt_feature::overlapNDTOccupancyScore(ref=self, mov, T) (ndt_feature_node.h:213-252)."""

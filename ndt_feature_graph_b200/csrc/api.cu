@@ -1239,6 +1239,27 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
   return rc;
 }
 
+int ndtb_map_write_jff(const ndtb_map *m, const char *path) {
+  if (!m || !path) return NDTB_ERR_ARG;
+  ndtb_grid g;
+  if (int rc = ndtb_map_grid(m, &g)) return rc;
+  const int64_t n = ndtb_map_num_cells(m, 0);
+  std::vector<ndtb_cell> cells((size_t)std::max<int64_t>(n, 1));
+  const int64_t k = n > 0 ? ndtb_map_export_cells(m, cells.data(), n, 0) : 0;
+  if (k < 0) return (int)k;
+  return ndtb_jff_write_cells(path, &g, cells.data(), k);
+}
+
+int ndtb_map_load_jff(ndtb_map *m, const char *path) {
+  if (!m || !path) return NDTB_ERR_ARG;
+  ndtb_grid g;
+  int64_t n = 0;
+  if (int rc = ndtb_jff_read_cells(path, &g, nullptr, 0, &n)) return rc;
+  std::vector<ndtb_cell> cells((size_t)std::max<int64_t>(n, 1));
+  if (int rc = ndtb_jff_read_cells(path, &g, cells.data(), n, &n)) return rc;
+  return ndtb_map_from_cells(m, &g, cells.data(), n, 1);
+}
+
 int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T, double *score) {
   DeviceGuard dev_guard(ctx);
   if (!ctx || !ref || !mov || !T || !score) return NDTB_ERR_ARG;

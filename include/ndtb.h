@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NDTB_VERSION 100
+#define NDTB_VERSION 101
 
 enum {
   NDTB_OK = 0,
@@ -86,6 +86,9 @@ typedef struct ndtb_params { /* NDTMatcherD2D public knobs + matchFusion flags *
                               registration; 0 = auto (1 for batches >= #SMs, up to 8 for small batches) */
   int32_t pass_budget;     /* engine knob: derivative passes a registration may use in the first (1-CTA) launch before
                               it is handed to a second launch on 8-CTA clusters (stragglers); 0 = auto, <0 = never */
+  int32_t planar;          /* 1 = NDTMatcherD2D_2D [upstream] (matchFusion2d, ndt_matcher_d2d_fusion.h:1159-1176):
+                              the same loop estimating (x, y, yaw) only */
+  int32_t reserved_;
 } ndtb_params;
 
 /* ndtb_result.status bits (SURVEY.md §5 "failure detection") */

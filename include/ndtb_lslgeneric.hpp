@@ -14,6 +14,7 @@
 //   lslgeneric::NDTCell {getMean,getCov,setMean,setCov,getCenter,getOccupancy,hasGaussian_}
 //   lslgeneric::NDTMatcherD2D {n_neighbours, ITR_MAX, DELTA_SCORE, step_control; match; covariance; derivativesNDT}
 //                                                                         ndt_feature_graph.cpp:261-298, ndt_matcher_d2d_fusion.h:856
+//   lslgeneric::NDTMatcherD2D_2D, ndt_feature::matchFusion2d              ndt_matcher_d2d_fusion.h:1159-1176
 //   lslgeneric::NDTMatcherP2D {match}                                      (no call site in the reference; BASELINE config C3)
 //   ndt_feature::matchFusion (NDT term + soft constraint / Tikhonov)       ndt_matcher_d2d_fusion.h:797-1155
 //   ndt_feature::overlapNDTOccupancyScore                                  ndt_feature_node.h:213-252
@@ -383,6 +384,7 @@ class NDTMatcherD2D {
     ndtb_default_params(&p);
     p.n_neighbours = n_neighbours, p.itr_max = ITR_MAX, p.delta_score = DELTA_SCORE;
     p.step_control = step_control, p.regularize = regularize;
+    p.planar = planar_ ? 1 : 0;
     return p;
   }
 
@@ -437,6 +439,16 @@ class NDTMatcherD2D {
     return out[0];
   }
   ndtb_result last = {};
+
+ protected:
+  bool planar_ = false;
+};
+
+// NDTMatcherD2D_2D [upstream]: the same matcher estimating (x, y, yaw) only; the reference reaches it through
+// matchFusion2d (ndt_matcher_d2d_fusion.h:1159-1176) when NDTFeatureFuserHMT::Params::fusion2d is set
+class NDTMatcherD2D_2D : public NDTMatcherD2D {
+ public:
+  NDTMatcherD2D_2D() { planar_ = true; }
 };
 
 // NDTMatcherP2D [upstream]: point cloud against an NDT map.  Not referenced by ndt_feature_graph itself (BASELINE
@@ -493,6 +505,18 @@ inline bool matchFusion(lslgeneric::NDTMap &targetNDT, lslgeneric::NDTMap &sourc
   if (ndtb::last_status() != NDTB_OK) return false;
   std::memcpy(ndtb::pose_data(T), r.T, sizeof r.T);
   return r.converged != 0;
+}
+
+// matchFusion2d (ndt_matcher_d2d_fusion.h:1159-1176): NDT-only, through NDTMatcherD2D_2D
+template <class Affine>
+inline bool matchFusion2d(lslgeneric::NDTMap &targetNDT, lslgeneric::NDTMap &sourceNDT, Affine &T, bool useInitialGuess,
+                          bool step_control, int ITR_MAX = 30, int n_neighbours = 2, double DELTA_SCORE = 10e-4) {
+  lslgeneric::NDTMatcherD2D_2D matcher_d2d_2d;
+  matcher_d2d_2d.n_neighbours = n_neighbours;
+  matcher_d2d_2d.step_control = step_control;
+  matcher_d2d_2d.ITR_MAX = ITR_MAX;
+  matcher_d2d_2d.DELTA_SCORE = DELTA_SCORE;
+  return matcher_d2d_2d.match(targetNDT, sourceNDT, T, useInitialGuess);
 }
 
 // overlapNDTOccupancyScore(ref, mov, T) on the maps of two nodes (ndt_feature_node.h:213-252)

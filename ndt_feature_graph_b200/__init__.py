@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     LazyGrid,
     NDTMap,
     NDTMatcherD2D,
+    NDTMatcherD2D_2D,
     NDTMatcherP2D,
     NdtbError,
     Params,

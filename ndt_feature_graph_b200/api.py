@@ -52,6 +52,8 @@ class Params(C.Structure):
         ("use_tikhonov", C.c_int32),
         ("ctas_per_match", C.c_int32),
         ("pass_budget", C.c_int32),
+        ("planar", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -470,3 +472,10 @@ class NDTMatcherP2D:
         self.e.check(self.e.L.ndtb_p2d_match(self.e.h, target.h, pts.ctypes.data, pts.shape[0], HOST, Tc.ctypes.data,
                                              C.byref(self.params), C.byref(r)))
         return r
+
+
+class NDTMatcherD2D_2D(NDTMatcherD2D):
+    """lslgeneric::NDTMatcherD2D_2D (matchFusion2d, ndt_matcher_d2d_fusion.h:1159-1176): D2D estimating (x, y, yaw) only."""
+
+    def __init__(self, engine, **knobs):
+        super().__init__(engine, planar=1, **knobs)

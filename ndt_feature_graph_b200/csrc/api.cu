@@ -474,7 +474,7 @@ int stage_points(ndtb_ctx *ctx, const float *pts, int64_t n, int mem, SlabP &out
 MatchConfig make_config(const ndtb_ctx *ctx, const ndtb_params *p, int max_tsize) {
   MatchConfig c;
   c.n_neighbours = p->n_neighbours;
-  c.itr_max = p->itr_max, c.step_control = p->step_control, c.regularize = p->regularize;
+  c.itr_max = p->itr_max, c.step_control = p->step_control, c.regularize = p->regularize, c.planar = p->planar;
   c.soft = p->use_soft_constraints, c.tik = p->use_tikhonov;
   c.delta_score = p->delta_score, c.lfd1 = p->lfd1, c.lfd2 = p->lfd2;
   // stage the block table in shared memory when it fits next to the optimiser state
@@ -728,6 +728,8 @@ void ndtb_default_params(ndtb_params *p) {
   p->use_tikhonov = 0;
   p->ctas_per_match = 0;
   p->pass_budget = 0;
+  p->planar = 0;
+  p->reserved_ = 0;
 }
 
 // ---- maps

@@ -431,7 +431,7 @@ match_kernel(const MatchJob *__restrict__ jobs, const int *__restrict__ job_ids,
     sh.grid = job.tgt.g;
     if (rank == 0) {
       OptParams &p = sh.prm;
-      p.itr_max = cfg.itr_max, p.step_control = cfg.step_control, p.regularize = cfg.regularize;
+      p.itr_max = cfg.itr_max, p.step_control = cfg.step_control, p.regularize = cfg.regularize, p.planar = cfg.planar;
       p.fusion = job.fusion, p.soft = job.fusion && cfg.soft, p.tik = job.fusion && cfg.tik;
       p.delta_score = cfg.delta_score;
       for (int i = 0; i < 36; i++) p.Q[i] = job.Q[i];

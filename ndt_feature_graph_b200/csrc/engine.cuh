@@ -85,7 +85,7 @@ struct MatchJob {
 
 struct MatchConfig {  // uniform over a batch
   int n_neighbours;
-  int itr_max, step_control, regularize, soft, tik;
+  int itr_max, step_control, regularize, soft, tik, planar;
   double delta_score, lfd1, lfd2;
   int table_smem_entries;  // capacity of the shared-memory staging area (hash entries); 0 = probe in global
 };

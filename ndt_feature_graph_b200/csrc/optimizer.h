@@ -32,6 +32,7 @@ struct Pose {
 
 struct OptParams {
   int itr_max, step_control, regularize;
+  int planar;  // NDTMatcherD2D_2D: estimate (x, y, yaw) only
   int fusion, soft, tik;
   double delta_score;
   double Q[36];  // Tcov^-1 (fusion only), row-major
@@ -512,6 +513,16 @@ NDTB_HDF inline void opt_advance(OptState &s, const OptParams &prm, const double
         for (int i = 0; i < 36; i++) H[i] = Hn[i];
         for (int i = 0; i < 6; i++) g[i] = gn[i];
         s.score_here += maha_score(s.x0, prm.Q);
+      }
+      if (prm.planar) {
+        // NDTMatcherD2D_2D [upstream] (matchFusion2d, fusion.h:1159-1176): z, roll and pitch are decoupled (zero gradient,
+        // unit diagonal), so their increments are exactly 0 and the (x, y, yaw) block is solved as a 3x3 system
+        const int drop[3] = {2, 3, 4};
+        for (int d = 0; d < 3; d++) {
+          g[drop[d]] = 0.0;
+          for (int j = 0; j < 6; j++) H[drop[d] * 6 + j] = H[j * 6 + drop[d]] = 0.0;
+          H[drop[d] * 6 + drop[d]] = 1.0;
+        }
       }
       for (int i = 0; i < 6; i++) s.scg[i] = g[i];
       if (s.score_here < s.score_best) s.Tbest = s.T, s.score_best = s.score_here;

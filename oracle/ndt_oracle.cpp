@@ -980,6 +980,18 @@ int match_cells(const orc_map &tgt, const std::vector<Gauss> &src, const double 
       std::memcpy(g, gn, sizeof g);
       score_here += maha_score(x0, Q);
     }
+    if (prm.planar) {
+      // NDTMatcherD2D_2D [upstream] (reached through matchFusion2d, ndt_matcher_d2d_fusion.h:1159-1176): the same
+      // Newton / More-Thuente loop on (x, y, yaw) only.  Restated as the 6-DoF system with z, roll and pitch decoupled
+      // (zero gradient, unit diagonal): their increments are exactly 0 and the 3x3 (x, y, yaw) block is solved and
+      // eigen-regularised exactly as the full system would be.
+      const int drop[3] = {2, 3, 4};
+      for (int d = 0; d < 3; d++) {
+        g[drop[d]] = 0.0;
+        for (int j = 0; j < 6; j++) H[drop[d] * 6 + j] = H[j * 6 + drop[d]] = 0.0;
+        H[drop[d] * 6 + drop[d]] = 1.0;
+      }
+    }
     double scg[6];
     for (int i = 0; i < 6; i++) scg[i] = g[i];
     if (score_here < score_best) {
@@ -1133,7 +1145,7 @@ void orc_default_params(orc_params *p) {
   p->use_soft_constraints = 0;
   p->use_tikhonov = 0;
   p->n_threads = 1;
-  p->pad_ = 0;
+  p->planar = 0;
 }
 
 orc_map *orc_map_create(double cx, double cy, double cz) {

@@ -36,7 +36,7 @@ class Params(C.Structure):
         ("use_soft_constraints", C.c_int32),
         ("use_tikhonov", C.c_int32),
         ("n_threads", C.c_int32),
-        ("pad_", C.c_int32),
+        ("planar", C.c_int32),
     ]
 
 

@@ -25,10 +25,10 @@ struct hh_result {
 };
 
 int hh_match(const double *T0, int itr_max, int step_control, int regularize, double delta_score, int fusion,
-             int soft, int tik, const double *Tcov36, hh_eval_cb cb, hh_result *out) {
+             int soft, int tik, const double *Tcov36, hh_eval_cb cb, hh_result *out, int planar) {
   OptParams prm;
   std::memset(&prm, 0, sizeof prm);
-  prm.itr_max = itr_max, prm.step_control = step_control, prm.regularize = regularize;
+  prm.itr_max = itr_max, prm.step_control = step_control, prm.regularize = regularize, prm.planar = planar;
   prm.delta_score = delta_score;
   prm.fusion = fusion, prm.soft = fusion && soft, prm.tik = fusion && tik;
   if (fusion && !inv6(Tcov36, prm.Q)) return -2;

@@ -24,13 +24,13 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/ndtb.h but not exported by libndtb.so"
     assert set(api.abi_symbols()) == set(names)  # the Python mirror binds exactly the declared ABI
-    assert L.ndtb_version() == 100
+    assert L.ndtb_version() == 101
 
 
 def test_struct_layouts():
     from ndt_feature_graph_b200 import api
 
-    assert C.sizeof(api.Params) == 56
+    assert C.sizeof(api.Params) == 64
     assert C.sizeof(api.Result) == 192 == api.RESULT_DTYPE.itemsize
     assert api.CELL_DTYPE.itemsize == 96
     for f, _ in api.Result._fields_:

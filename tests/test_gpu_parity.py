@@ -414,3 +414,31 @@ def test_pass_budget_handover_with_split_covariance(oracle, engine, c2small):
         if ro.pose_changed:
             _, co = oracle.d2d_covariance(om[0], om[1], ro.pose())
             np.testing.assert_allclose(cb_[i], co, rtol=1e-5, atol=1e-9 * np.abs(co).max())
+
+
+def test_planar_matcher(oracle, engine, golden, oracle_fixture_maps, gpu_fixture_maps, c1):
+    """NDTMatcherD2D_2D (matchFusion2d, ndt_matcher_d2d_fusion.h:1159-1176): (x, y, yaw) only."""
+    import ndt_feature_graph_b200 as N
+
+    m = N.NDTMatcherD2D_2D(engine, delta_score=1e-6)
+    p = oracle.default_params(planar=1, delta_score=1e-6)
+    n = 0
+    for k in range(7):
+        for T0 in (golden[f"Todom{k}"], synth.pose2d(0.03, -0.02, 0.01) @ golden[f"Tfuse{k}"]):
+            ro = oracle.d2d_match(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T0, p)
+            if not oracle.d2d_is_stable(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T0, base=ro, planar=1, delta_score=1e-6):
+                continue
+            n += 1
+            rg = m.match(gpu_fixture_maps[k], gpu_fixture_maps[k + 1], T0)
+            # (pass counters are not compared: with three eigenvalues the iteration is more sensitive to the last bits of
+            # the sums than the 6-DoF one, a line search may take one evaluation more on the way to the same pose)
+            assert synth.pose_error(ro.pose(), rg.pose()) < 1e-4 and ro.converged == rg.converged
+            Tg = rg.pose()
+            assert Tg[2, 3] == T0[2, 3] and np.array_equal(Tg[2, :3], T0[2, :3])
+    assert n >= 10
+    ca, cb, D, om, gm = c1
+    T0 = synth.perturb_pose(D, 4, dt=0.03, dr=0.005, planar=True)  # (from 0.1 m the 3-DoF iteration often stalls short of the optimum)
+    ro = oracle.d2d_match(om[0], om[1], T0, oracle.default_params(planar=1))
+    rg = N.NDTMatcherD2D_2D(engine).match(gm[0], gm[1], T0)
+    assert synth.pose_error(ro.pose(), rg.pose()) < 1e-4 and ro.converged == rg.converged
+    assert synth.pose_error(rg.pose(), D) < 0.02

@@ -206,9 +206,13 @@ def run_gpu(args):
 
     comm_stream = torch.cuda.Stream(dev) if world > 1 else None
 
+    step_sync = lanes > 1  # with several lanes every lane waits for its own step before enqueuing its next one
+
     def step_device(k=0):
         engs_d[k].register_scans_raw(B, tp, tn, sp, sn, T0c.ctypes.data, CELL, -1.0, prm, True, api.DEVICE, api.DEVICE,
                                      d_ress[k].data_ptr(), d_covs[k].data_ptr())
+        if step_sync:
+            engs_d[k].synchronize()
 
     def gather_step(records, ev):
         # the only cross-GPU step: gather of the per-edge result records (NCCL over NVLink), always issued by the main
@@ -424,7 +428,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) leg: profiling runs only")
-    ap.add_argument("--lanes", type=int, default=1, help="contexts (host thread + stream each) the device-resident leg alternates its steps between")
+    ap.add_argument("--lanes", type=int, default=2, help="contexts (host thread + stream each) the device-resident leg alternates its steps between")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="contexts (host threads) the e2e leg alternates its steps between")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the step timed on the CPU (0 = auto, ~10-30 s)")
     args = ap.parse_args()

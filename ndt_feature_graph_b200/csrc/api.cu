@@ -1231,7 +1231,13 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
   std::vector<const ndtb_map *> tg((size_t)n_pairs), sr((size_t)n_pairs);
   for (int64_t e = 0; e < n_pairs; e++) {
     tg[e] = maps[2 * e], sr[e] = maps[2 * e + 1];
-    if (!maps[2 * e]->grid_ready || !maps[2 * e + 1]->grid_ready) return NDTB_ERR_EMPTY;
+    // A scan without a single usable point defines no grid.  One bad scan must not fail the whole batch (the reference
+    // would run the other edges): it becomes an empty one-voxel map, its registration leaves the pose unchanged and
+    // reports NDTB_ST_NO_CELLS.
+    for (int q = 0; q < 2; q++) {
+      ndtb_map *m = maps[2 * e + q];
+      if (!m->grid_ready) m->set_grid(0.0, 0.0, 0.0, cell, cell, cell);
+    }
   }
   const int rc = match_batch_impl(ctx, n_pairs, tg.data(), sr.data(), T0s, nullptr, p, with_covariance && cov36s, out_mem, res, cov36s);
   pt.mark("match+cov");

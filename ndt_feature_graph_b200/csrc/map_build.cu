@@ -422,7 +422,10 @@ __global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restric
 // NDTCell::computeGaussian), merge with the stored (N, mean, cov), occupancy.  Cells whose covariance has to go through
 // rescaleCovariance are appended to the map's eigen list (the dead `cursor` array) and finished by k_eigen: the 3x3
 // Jacobi iteration is a long serial fp64 chain that wants many resident warps, the gather loops here want registers.
-__global__ void __launch_bounds__(128) k_cells(const BuildJob *__restrict__ jobs) {
+#ifndef NDTB_KCELLS_MINBLOCKS
+#define NDTB_KCELLS_MINBLOCKS 8  // resident CTAs per SM the register allocation of k_cells is sized for (64 registers; measured 1 -> 8: -0.7 ms per 1184 maps)
+#endif
+__global__ void __launch_bounds__(128, NDTB_KCELLS_MINBLOCKS) k_cells(const BuildJob *__restrict__ jobs) {
   const BuildJob &j = jobs[blockIdx.y];
   const float4 *__restrict__ pts = j.pts;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < j.n_all; c += gridDim.x * blockDim.x) {

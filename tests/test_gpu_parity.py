@@ -442,3 +442,17 @@ def test_planar_matcher(oracle, engine, golden, oracle_fixture_maps, gpu_fixture
     rg = N.NDTMatcherD2D_2D(engine).match(gm[0], gm[1], T0)
     assert synth.pose_error(ro.pose(), rg.pose()) < 1e-4 and ro.converged == rg.converged
     assert synth.pose_error(rg.pose(), D) < 0.02
+
+
+def test_register_scans_tolerates_an_empty_scan(oracle, engine, c2small):
+    """One scan of a batch has no usable point: its edge reports NO_CELLS and keeps the guess, the others are unaffected."""
+    ca, cb, D, om, gm = c2small
+    T0 = synth.perturb_pose(D, 77)
+    bad = np.full((50, 4), np.nan, np.float32)
+    res, cov = engine.register_scans([ca, ca, bad], [cb, bad, cb], [T0, T0, T0], cell=0.5, with_covariance=True)
+    ref, _ = engine.register_scans([ca], [cb], [T0], cell=0.5, with_covariance=True)
+    assert np.array_equal(res["T"][0], ref["T"][0])
+    for e in (1, 2):
+        assert res["status"][e] & 16 and res["pose_changed"][e] == 0  # NDTB_ST_NO_CELLS
+        assert np.array_equal(res["T"][e].reshape(4, 4).T, T0)
+        assert np.array_equal(cov[e], 0.02 * np.eye(6))  # ndt_feature_graph.cpp:300-310

@@ -421,14 +421,14 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=592, help="scan pairs per step per GPU")
     ap.add_argument("--base", type=int, default=8, help="ray-cast base scenes per rank")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) leg: profiling runs only")
-    ap.add_argument("--lanes", type=int, default=2, help="contexts (host thread + stream each) the device-resident leg alternates its steps between")
+    ap.add_argument("--lanes", type=int, default=3, help="contexts (host thread + stream each) the device-resident leg alternates its steps between")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="contexts (host threads) the e2e leg alternates its steps between")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the step timed on the CPU (0 = auto, ~10-30 s)")
     args = ap.parse_args()

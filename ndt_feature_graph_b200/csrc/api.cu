@@ -37,6 +37,7 @@ using namespace ndtb;
 
 struct ndtb_ctx {
   int device = 0;
+  cudaMemPool_t pool = nullptr;  // the context's own stream-ordered pool: no reuse dependencies between contexts
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 0;
@@ -105,7 +106,7 @@ using SlabP = std::shared_ptr<Slab>;
 int slab_alloc(ndtb_ctx *ctx, size_t bytes, SlabP &out) {
   out = std::make_shared<Slab>(ctx);
   out->bytes = bytes ? bytes : 256;
-  CU_TRY(ctx, cudaMallocAsync((void **)&out->p, out->bytes, ctx->stream));
+  CU_TRY(ctx, cudaMallocFromPoolAsync((void **)&out->p, out->bytes, ctx->pool, ctx->stream));
   return NDTB_OK;
 }
 
@@ -664,11 +665,22 @@ int ndtb_ctx_create(int device, void *stream, ndtb_ctx **out) {
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;  // keep freed slabs cached: allocation becomes a pointer bump after warm-up
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  // A private pool per context: contexts driven concurrently (one per host thread) would otherwise hand each other's
+  // freed slabs around through the device's default pool, which makes the driver insert cross-stream dependencies (or fall
+  // back to a synchronising cudaMalloc) and serialises them.  Freed slabs stay cached: after warm-up an allocation is a
+  // pointer bump.
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) {
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return NDTB_ERR_CUDA;
   }
+  uint64_t thr = UINT64_MAX;
+  cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
   *out = c;
   return NDTB_OK;
 }
@@ -683,6 +695,7 @@ void ndtb_ctx_destroy(ndtb_ctx *ctx) {
   for (cudaEvent_t e : ctx->aux_ev)
     if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }
 

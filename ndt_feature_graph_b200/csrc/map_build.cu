@@ -377,6 +377,15 @@ __device__ void warp_radix_sort(int *a, int *b, int n, int bits, int *hist /*256
   }
 }
 
+__device__ __forceinline__ int nth_set_bit(unsigned long long m, int k) {  // position of the k-th (0-based) set bit
+  const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+  const int pl = __popc(lo);
+  return k < pl ? (int)__fns(lo, 0, k + 1) : 32 + (int)__fns(hi, 0, k - pl + 1);
+}
+
+// The metadata of up to 32 cells of a block (count, segment offset, voxel key) is fetched by the lanes in parallel and
+// the ids of the next small cell are loaded while the current one is being ranked: one dependent round trip per cell
+// instead of three.
 __global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restrict__ jobs) {
   __shared__ int sbuf[8][256];
   const BuildJob &j = jobs[blockIdx.y];
@@ -386,33 +395,48 @@ __global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restric
   const int bits = 32 - __clz(j.npts > 1 ? j.npts - 1 : 1);
   for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ntb; t += gridDim.x * 8) {
     const int b = j.tb_list[t];
-    unsigned long long m = j.amask[b];
-    int c = j.abase[b];
-    for (; m; m &= m - 1ull, c++) {
-      if (lane == 0) j.cell_key[c] = b * 64 + (__ffsll((long long)m) - 1);
-      const int n = j.cnt[c];
-      if (n == 0) continue;
-      int *seg = j.seg_idx + j.seg_off[c];
-      int *srt = j.seg2 + j.seg_off[c];
-      if (n <= 32) {  // ranks by 32 broadcasts
-        const int v = lane < n ? seg[lane] : 0x7fffffff;
-        int r = 0;
-        for (int q = 0; q < n; q++) r += __shfl_sync(FULL, v, q) < v;
-        if (lane < n) srt[r] = v;
-      } else if (n <= SORT_BITONIC_MAX) {  // 64-element bitonic network in shared memory
-        for (int e = lane; e < 64; e += 32) sb[e] = e < n ? seg[e] : 0x7fffffff;
-        __syncwarp();
-        for (int k = 2; k <= 64; k <<= 1)
-          for (int jj = k >> 1; jj > 0; jj >>= 1) {
-            const int i0 = 2 * lane - (lane & (jj - 1)), i1 = i0 + jj;
-            const int a0 = sb[i0], a1 = sb[i1];
-            if ((a0 > a1) == ((i0 & k) == 0)) sb[i0] = a1, sb[i1] = a0;
+    const unsigned long long m = j.amask[b];
+    const int c0 = j.abase[b], nc = __popcll(m);
+    for (int base = 0; base < nc; base += 32) {
+      const int ci = base + lane;
+      int my_n = 0, my_off = 0;
+      if (ci < nc) {
+        my_n = j.cnt[c0 + ci], my_off = j.seg_off[c0 + ci];
+        j.cell_key[c0 + ci] = b * 64 + nth_set_bit(m, ci);
+      }
+      const int nround = min(32, nc - base);
+      int n = __shfl_sync(FULL, my_n, 0), off = __shfl_sync(FULL, my_off, 0);
+      int v = (lane < n && n <= 32) ? j.seg_idx[off + lane] : 0x7fffffff;
+      for (int q = 0; q < nround; q++) {
+        int n2 = 0, off2 = 0, v2 = 0x7fffffff;
+        if (q + 1 < nround) {
+          n2 = __shfl_sync(FULL, my_n, q + 1), off2 = __shfl_sync(FULL, my_off, q + 1);
+          if (lane < n2 && n2 <= 32) v2 = j.seg_idx[off2 + lane];
+        }
+        if (n > 0) {
+          int *seg = j.seg_idx + off;
+          int *srt = j.seg2 + off;
+          if (n <= 32) {  // ranks by n broadcasts
+            int r = 0;
+            for (int e = 0; e < n; e++) r += __shfl_sync(FULL, v, e) < v;
+            if (lane < n) srt[r] = v;
+          } else if (n <= SORT_BITONIC_MAX) {  // 64-element bitonic network in shared memory
+            for (int e = lane; e < 64; e += 32) sb[e] = e < n ? seg[e] : 0x7fffffff;
             __syncwarp();
+            for (int k = 2; k <= 64; k <<= 1)
+              for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                const int i0 = 2 * lane - (lane & (jj - 1)), i1 = i0 + jj;
+                const int a0 = sb[i0], a1 = sb[i1];
+                if ((a0 > a1) == ((i0 & k) == 0)) sb[i0] = a1, sb[i1] = a0;
+                __syncwarp();
+              }
+            for (int e = lane; e < n; e += 32) srt[e] = sb[e];
+            __syncwarp();
+          } else {  // any size: stable radix sort through global memory (L1/L2 resident segments)
+            warp_radix_sort(seg, srt, n, bits, sb, lane);
           }
-        for (int e = lane; e < n; e += 32) srt[e] = sb[e];
-        __syncwarp();
-      } else {  // any size: stable radix sort through global memory (L1/L2 resident segments)
-        warp_radix_sort(seg, srt, n, bits, sb, lane);
+        }
+        n = n2, off = off2, v = v2;
       }
     }
   }

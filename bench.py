@@ -388,7 +388,8 @@ def run_gpu(args):
                          "frac": alg_bytes_launch / t_launch / 1e9 / hbm, "peak_source": hbm_src,
                          # dram__bytes_read+write of the two launches of one 592-pair step, ncu --set full capture
                          # profiles/r01b_match_kernel_ncu_full.csv (GB per step; scales with pairs per step)
-                         "traffic": 3.196 * B / 592.0,
+                         "traffic": 3.196 * B / 592.0, "traffic_unit": "GB per step (both launches of the kernel)",
+                         "algorithmic_gb_per_step": alg_bytes_launch / 1e9,
                          "launch_ms": 1e3 * t_launch, "share_of_step": 1e3 * t_launch / solo_ms, "step_ms_one_lane": solo_ms,
                          "note": "working set is L1/L2 resident; the binding limit is fp64 CUDA-core throughput, see DESIGN.md"},
         }

@@ -280,9 +280,11 @@ def run_gpu(args):
     # roofline of the dominant kernel: its launches timed alone (one lane), CUDA events inside the library
     eng.enable_timing(True)
     eng.match_time()
+    eng.build_time()
     for _ in range(max(2, min(args.steps, 3))):
         step_device(0)
     match_ms, match_n = eng.match_time()
+    build_ms, build_n = eng.build_time()
     eng.enable_timing(False)
     sync_all()
     solo0, solo1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -393,6 +395,13 @@ def run_gpu(args):
                          "launch_ms": 1e3 * t_launch, "share_of_step": 1e3 * t_launch / solo_ms, "step_ms_one_lane": solo_ms,
                          "note": "working set is L1/L2 resident; the binding limit is fp64 CUDA-core throughput, see DESIGN.md"},
         }
+        # kernel (i), the bandwidth-bound one by design: B_build = 16 P + 80 C per map
+        alg_build = float(in_bytes) + 80.0 * float((res["n_src_cells"] + res["n_tgt_cells"]).sum())
+        t_build = 1e-3 * build_ms / max(build_n, 1)
+        line["roofline_build"] = {"kernel": "map build (13 launches of kernel i per step, 2 maps per pair)", "bound": "hbm",
+                                  "achieved": alg_build / t_build / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "frac": alg_build / t_build / 1e9 / hbm, "build_ms": 1e3 * t_build,
+                                  "note": "latency-bound by the order-exact per-cell chains, see DESIGN.md"}
         if world == 1 and not args.no_cpu:
             cores = host_cores()
             # bounded sample: ~0.6 core-seconds per C2 pair -> 10-30 s of wall time on the box's cores

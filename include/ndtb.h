@@ -135,6 +135,8 @@ int ndtb_ctx_sm_count(const ndtb_ctx *ctx);
  * returns the accumulated milliseconds and launch count since the last call, and resets both. */
 int ndtb_ctx_enable_timing(ndtb_ctx *ctx, int on);
 int ndtb_ctx_match_time(ndtb_ctx *ctx, double *ms, int64_t *launches);
+/* the same for batched map builds from device-resident points (all kernels of kernel (i), host waits included) */
+int ndtb_ctx_build_time(ndtb_ctx *ctx, double *ms, int64_t *calls);
 void ndtb_default_params(ndtb_params *p);
 
 /* ---- maps: lslgeneric::NDTMap(new LazyGrid(cell)) --------------------------------------------- */

@@ -113,6 +113,7 @@ def load_library():
         "ndtb_ctx_sm_count": (C.c_int, [vp]),
         "ndtb_ctx_enable_timing": (C.c_int, [vp, C.c_int]),
         "ndtb_ctx_match_time": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(i64)]),
+        "ndtb_ctx_build_time": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(i64)]),
         "ndtb_default_params": (None, [PP]),
         "ndtb_map_create": (C.c_int, [vp, dbl, dbl, dbl, C.POINTER(vp)]),
         "ndtb_map_destroy": (None, [vp]),
@@ -237,6 +238,12 @@ class Engine:
         """(milliseconds, launches) of the registration kernel since the last call (synchronises)."""
         ms, n = C.c_double(0), C.c_int64(0)
         self.check(self.L.ndtb_ctx_match_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def build_time(self):
+        """(milliseconds, calls) of the batched map builds since the last call (synchronises)."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        self.check(self.L.ndtb_ctx_build_time(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     def register_scans_raw(self, n, tgt_ptrs, n_tgt, src_ptrs, n_src, T0s_cm, cell, range_limit, params, with_covariance,

@@ -46,6 +46,7 @@ struct ndtb_ctx {
   std::string last_error;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;  // event pairs around match-kernel launches
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed_build;  // event pairs around batched map builds
   // host-buffer path: scans are uploaded on a second stream in chunks while the previous chunk's maps are being built
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> copy_events;
@@ -727,6 +728,22 @@ int ndtb_ctx_match_time(ndtb_ctx *ctx, double *ms, int64_t *launches) {
   ctx->timed.clear();
   return NDTB_OK;
 }
+int ndtb_ctx_build_time(ndtb_ctx *ctx, double *ms, int64_t *calls) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !ms) return NDTB_ERR_ARG;
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  double tot = 0;
+  for (auto &pr : ctx->timed_build) {
+    float t = 0;
+    CU_TRY(ctx, cudaEventElapsedTime(&t, pr.first, pr.second));
+    tot += t;
+    cudaEventDestroy(pr.first), cudaEventDestroy(pr.second);
+  }
+  *ms = tot;
+  if (calls) *calls = (int64_t)ctx->timed_build.size();
+  ctx->timed_build.clear();
+  return NDTB_OK;
+}
 int ndtb_ctx_sm_count(const ndtb_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
 void ndtb_default_params(ndtb_params *p) {
@@ -886,7 +903,17 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
   if (mem == NDTB_MEM_DEVICE) {
     std::vector<char> load((size_t)n_maps, 1);
     std::vector<double> range((size_t)n_maps, range_limit);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->timing) {
+      CU_TRY(ctx, cudaEventCreate(&ev0));
+      CU_TRY(ctx, cudaEventCreate(&ev1));
+      CU_TRY(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
     const int rc = build_batch(ctx, mv, ps, load, range, maxnumpoints, occupancy_limit);
+    if (ctx->timing) {
+      CU_TRY(ctx, cudaEventRecord(ev1, ctx->stream));
+      ctx->timed_build.push_back({ev0, ev1});
+    }
     pt.mark("build_batch");
     return rc;
   }

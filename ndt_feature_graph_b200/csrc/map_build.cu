@@ -202,20 +202,42 @@ __global__ void k_extent(const BuildJob *__restrict__ jobs, const int *__restric
 }
 
 // ---- binning -----------------------------------------------------------------------------------------
+// Four points per thread and iteration, all loads of a stage issued before the first use: the kernel is bound by the
+// latency of the dependent mask look-up, not by bytes.
 __global__ void k_mark(const BuildJob *__restrict__ jobs) {
   const BuildJob &j = jobs[blockIdx.y];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
-    const float4 p = j.pts[i];
-    int key = -1, ix, iy, iz;
-    if (!pt_skip(p, j.range_limit) && voxel_index(j.g, (double)p.x, (double)p.y, (double)p.z, ix, iy, iz) &&
-        in_grid(j.g, ix, iy, iz)) {
-      const int b = block_id(j.g, ix, iy, iz), bit = block_bit(ix, iy, iz);
-      key = b * 64 + bit;
-      // ~90 % of the points fall into a voxel that is already marked: look before taking the (contended) atomic.  A stale
-      // read only costs a redundant atomicOr.
-      if (!((__ldcg(j.amask + b) >> bit) & 1ull)) atomicOr(j.amask + b, 1ull << bit);
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < j.npts; i0 += 4 * stride) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * stride;
+      p[u] = i < j.npts ? j.pts[i] : make_float4(nanf(""), 0.f, 0.f, 0.f);
     }
-    j.pt_cell[i] = key;
+    int key[4], b[4], bit[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int ix, iy, iz;
+      key[u] = -1, b[u] = 0, bit[u] = 0;
+      if (!pt_skip(p[u], j.range_limit) && voxel_index(j.g, (double)p[u].x, (double)p[u].y, (double)p[u].z, ix, iy, iz) &&
+          in_grid(j.g, ix, iy, iz)) {
+        b[u] = block_id(j.g, ix, iy, iz), bit[u] = block_bit(ix, iy, iz);
+        key[u] = b[u] * 64 + bit[u];
+      }
+    }
+    // ~90 % of the points fall into a voxel that is already marked: look before taking the (contended) atomic.  A stale
+    // read only costs a redundant atomicOr.
+    unsigned long long m[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) m[u] = key[u] >= 0 ? __ldcg(j.amask + b[u]) : ~0ull;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (key[u] >= 0 && !((m[u] >> bit[u]) & 1ull)) atomicOr(j.amask + b[u], 1ull << bit[u]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * stride;
+      if (i < j.npts) j.pt_cell[i] = key[u];
+    }
   }
 }
 
@@ -265,13 +287,28 @@ __global__ void __launch_bounds__(1024) k_blockscan(const BuildJob *__restrict__
 
 __global__ void k_count(const BuildJob *__restrict__ jobs) {
   const BuildJob &j = jobs[blockIdx.y];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
-    const int key = j.pt_cell[i];
-    if (key < 0) continue;
-    const int b = key >> 6, bit = key & 63;
-    const int c = j.abase[b] + __popcll(j.amask[b] & ((1ull << bit) - 1ull));
-    j.pt_cell[i] = c;
-    j.seg2[i] = atomicAdd(j.cnt + c, 1);  // arrival rank inside the cell (arbitrary order; k_sort_segments orders the ids)
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < j.npts; i0 += 4 * stride) {
+    int key[4], base[4];
+    unsigned long long m[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * stride;
+      key[u] = i < j.npts ? j.pt_cell[i] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      base[u] = 0, m[u] = 0ull;
+      if (key[u] >= 0) base[u] = j.abase[key[u] >> 6], m[u] = j.amask[key[u] >> 6];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (key[u] < 0) continue;
+      const int i = i0 + u * stride;
+      const int c = base[u] + __popcll(m[u] & ((1ull << (key[u] & 63)) - 1ull));
+      j.pt_cell[i] = c;
+      j.seg2[i] = atomicAdd(j.cnt + c, 1);  // arrival rank inside the cell (arbitrary order; k_sort_segments orders the ids)
+    }
   }
 }
 

@@ -440,7 +440,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) leg: profiling runs only")
     ap.add_argument("--lanes", type=int, default=3, help="contexts (host thread + stream each) the device-resident leg alternates its steps between")
-    ap.add_argument("--e2e-lanes", type=int, default=2, help="contexts (host threads) the e2e leg alternates its steps between")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="contexts (host threads) the e2e leg alternates its steps between")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the step timed on the CPU (0 = auto, ~10-30 s)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -94,3 +94,52 @@ def test_facade_corridor_matches_oracle(facade_bin, oracle, tmp_path):
         so = oracle.overlap_occupancy_score(om[a], om[b], Tl)
         assert abs(r[f"link{i}_score"] - so) <= 1e-12 * max(1.0, abs(so))
     assert np.array_equal(_cm(r["link2_T"]), T0s[2])
+
+
+def _write_saved_graph(golden, tmp_path):
+    """What the fuser saves per node (ndt_feature_fuser_hmt.cpp:20-49): mapping{k}.jff + mapping{k}local_odom.T, rebuilt
+    from the golden extraction of the shipped files with the library's own JFF writer."""
+    from conftest import fixture_cells
+    from ndt_feature_graph_b200 import api
+
+    for k in range(8):
+        center, cell, size, cells = fixture_cells(golden, k, api.CELL_DTYPE)
+        api.jff_write_cells(tmp_path / f"mapping{k}.jff", center, cell, size, cells)
+        if k < 7:
+            T = golden[f"Todom{k}"]
+            with open(tmp_path / f"mapping{k}local_odom.T", "w") as f:  # boost text archive: header tokens, then 16 numbers
+                f.write("22 serialization::archive 10 0 0 " + " ".join(repr(float(v)) for v in T.T.ravel()) + "\n")
+    return str(tmp_path / "mapping")
+
+
+def test_example_compiles_and_fails_loudly_without_device(golden, tmp_path):
+    import torch
+
+    import __graft_entry__ as g
+
+    exe = g.build_example()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_example_refines_saved_graph")
+    out = subprocess.run([exe, _write_saved_graph(golden, tmp_path), "8"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 1 and "no CUDA device" in out.stderr
+
+
+@pytest.mark.gpu
+def test_example_refines_saved_graph(golden, oracle, oracle_fixture_maps, tmp_path):
+    """examples/refine_edges.cpp end to end: JFF node maps from disk -> facade -> one batched edge refinement."""
+    import re
+
+    import __graft_entry__ as g
+
+    out = subprocess.run([g.build_example(), _write_saved_graph(golden, tmp_path), "8"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    links = re.findall(r"link (\d+) -> (\d+): x (\S+) y (\S+) yaw (\S+)  converged (\d)  score (\S+)", out.stdout)
+    assert len(links) == 7
+    for k, (a, b, x, y, yaw, conv, score) in enumerate(links):
+        ro = oracle.d2d_match(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], golden[f"Todom{k}"])
+        T = ro.pose()
+        assert (int(a), int(b), int(conv)) == (k, k + 1, ro.converged)
+        assert abs(float(x) - T[0, 3]) < 2e-4 and abs(float(y) - T[1, 3]) < 2e-4  # printed with 4 decimals
+        assert abs(float(yaw) - np.arctan2(T[1, 0], T[0, 0])) < 2e-4
+        so = oracle.overlap_occupancy_score(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T)
+        assert abs(float(score) - so) < 2e-4

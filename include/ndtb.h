@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NDTB_VERSION 101
+#define NDTB_VERSION 200
 
 enum {
   NDTB_OK = 0,
@@ -152,8 +152,17 @@ int ndtb_map_initialize(ndtb_map *m, double cx, double cy, double cz, double sx,
  * (pcl::PointXYZ: x,y,z,pad), in host or device memory.  *n_binned (optional) = points kept. */
 int ndtb_map_load_point_cloud(ndtb_map *m, const float *pts, int64_t n, double range_limit, int mem,
                               int64_t *n_binned);
-/* NDTMap::addPointCloud, end-point binning only (no ray tracing — SURVEY.md §8f rank 1) */
+/* NDTMap::addPointCloud, end-point binning only (no ray tracing; see ndtb_map_add_point_cloud) */
 int ndtb_map_add_points(ndtb_map *m, const float *pts, int64_t n, int mem, int64_t *n_binned);
+/* NDTMap::addPointCloud(origin, pc, classifierTh, maxz, sensor_noise, occupancy_limit) [upstream] WITH the free-space ray
+ * trace (LazyGrid::traceLine) and the occupancy update of the cells every ray meets — the call the fuser makes on the node
+ * map, ndt_feature_fuser_hmt.cpp:92 (initialize: 0.1, 100.0, 0.1) and :485 (update: 0.06, 25).  origin = 3 doubles
+ * (sensor position in the map frame).  The rays are traced when ndtb_map_compute_cells runs (the reference calls the two
+ * back to back); at most 4 addPointCloud calls may be pending.  Cells met by a ray exist afterwards (occupancy < 0) like
+ * the cells of an initialize()d LazyGrid; on a lazily allocated grid upstream would additionally drop a fake point into
+ * every cell a ray creates, which is not restated (never reached from the reference's call sites). */
+int ndtb_map_add_point_cloud(ndtb_map *m, const double *origin, const float *pts, int64_t n, int mem, double classifier_th,
+                             double maxz, double sensor_noise, double occupancy_limit);
 /* NDTMap::computeNDTCells(CELL_UPDATE_MODE_SAMPLE_VARIANCE, maxnumpoints, occupancy_limit) */
 int ndtb_map_compute_cells(ndtb_map *m, uint32_t maxnumpoints, float occupancy_limit);
 /* Batched loadPointCloud + computeNDTCells over n_maps maps in a handful of launches (front-end and
@@ -217,6 +226,56 @@ int ndtb_jff_read_cells(const char *path, ndtb_grid *g, ndtb_cell *cells, int64_
 /* the same for a map resident in HBM (export + write / read + ndtb_map_from_cells); 0 on success like upstream */
 int ndtb_map_write_jff(const ndtb_map *m, const char *path);
 int ndtb_map_load_jff(ndtb_map *m, const char *path);
+
+/* lslgeneric::transformPointCloudInPlace [upstream]: the pose is cast to float and applied in float arithmetic
+ * (ndt_feature_fuser_hmt.cpp:75-76,191,479).  in / out: n x 4 float in `in_mem` / `out_mem` memory (may alias). */
+int ndtb_transform_point_cloud(ndtb_ctx *ctx, const double *T16, const float *in, int64_t n, int in_mem, float *out,
+                               int out_mem);
+
+/* ---- front end: NDTFeatureFuserHMT (ndt_feature/src/ndt_feature_src/ndt_feature_fuser_hmt.cpp) ----------------------
+ * The per-scan step of the reference with useNDT only (useFeat = useOdom = false, loadCentroid = false: what every
+ * offline configuration sets — ndt_graph_offline.cpp:306-317): the node map lives in HBM and is updated in place.
+ *   initialize  :65-102   map->initialize + addPointCloud(origin, cloud, 0.1, 100, 0.1) + computeNDTCells(1e5, 255)
+ *   update      :108-512  local map of the scan (:195-227) -> matchFusion vs the node map (:352-358) -> covariance
+ *                         (:399-420) -> pose bookkeeping (:436-474) -> ray-traced addPointCloud(origin, cloud, 0.06, 25)
+ *                         + computeNDTCells(1e5, 255) (:482-487)                                                      */
+typedef struct ndtb_fuser ndtb_fuser;
+typedef struct ndtb_fuser_params { /* NDTFeatureFuserHMT::Params (ndt_feature_fuser_hmt.h:58-207) + sensor pose + motion model */
+  double resolution, map_size_x, map_size_y, map_size_z, sensor_range;
+  double max_translation_norm, max_rotation_norm;
+  double delta_score;            /* DELTA_SCORE */
+  int32_t neighbours, itr_max;   /* neighbours, ITR_MAX */
+  int32_t step_control;          /* stepcontrol */
+  int32_t global_transf;         /* globalTransf */
+  int32_t use_soft_constraints, use_tikhonov, compute_cov, fusion2d;
+  int32_t all_matches_valid, fuse_incomplete, check_consistency, force_odom_as_est;
+  double sensor_pose[16];        /* column-major 4x4 (setSensorPose) */
+  double motion[6];              /* MotionModel2d::Params Cd, Ct, Dd, Dt, Td, Tt (motion_model.hpp:123-163) */
+} ndtb_fuser_params;
+void ndtb_fuser_default_params(ndtb_fuser_params *p);
+int ndtb_fuser_create(ndtb_ctx *ctx, const ndtb_fuser_params *p, ndtb_fuser **out);
+void ndtb_fuser_destroy(ndtb_fuser *f);
+/* cloud = n x 4 float in the SENSOR frame (host or device memory) */
+int ndtb_fuser_initialize(ndtb_fuser *f, const double *init_pose16, const float *cloud, int64_t n, int mem);
+/* Tnow16 (out), res (optional: the registration record), cov36 (optional, row-major; zero when !compute_cov) */
+int ndtb_fuser_update(ndtb_fuser *f, const double *Tmotion16, const float *cloud, int64_t n, int mem, int update_ndt_map,
+                      double *Tnow16, ndtb_result *res, double *cov36);
+ndtb_map *ndtb_fuser_map(ndtb_fuser *f); /* the node map (owned by the fuser) */
+int ndtb_fuser_pose(const ndtb_fuser *f, double *Tnow16);
+
+/* ---- NDTFeatureGraph front end (ndt_feature/src/ndt_feature_src/ndt_feature_graph.cpp:24-144): a chain of nodes, each
+ * a fuser with its own map in its own frame; a new node is spawned when the odometric path length inside the current
+ * node exceeds new_node_transl_dist (the last scan is registered against the old node without being fused). */
+typedef struct ndtb_graph ndtb_graph;
+int ndtb_graph_create(ndtb_ctx *ctx, const ndtb_fuser_params *p, double new_node_transl_dist, ndtb_graph **out);
+void ndtb_graph_destroy(ndtb_graph *g);
+int ndtb_graph_set_new_node_dist(ndtb_graph *g, double new_node_transl_dist);
+int ndtb_graph_initialize(ndtb_graph *g, const double *init_pose16, const float *cloud, int64_t n, int mem);
+int ndtb_graph_update(ndtb_graph *g, const double *Tmotion16, const float *cloud, int64_t n, int mem, double *Tnow16);
+int64_t ndtb_graph_num_nodes(const ndtb_graph *g);
+/* node k: pose T, Tlocal_odom, Tlocal_fuse (16 doubles each, optional), its map (borrowed), number of fused scans */
+int ndtb_graph_node(ndtb_graph *g, int64_t k, double *T16, double *Tlocal_odom16, double *Tlocal_fuse16, ndtb_map **map,
+                    int32_t *nb_updates);
 
 /* ndt_feature::overlapNDTOccupancyScore(ref, mov, T) */
 int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T,

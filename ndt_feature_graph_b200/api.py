@@ -80,6 +80,20 @@ class Result(C.Structure):
         return np.array(self.T, dtype=np.float64).reshape(4, 4).T.copy()
 
 
+class FuserParams(C.Structure):
+    """ndtb_fuser_params: NDTFeatureFuserHMT::Params (ndt_feature_fuser_hmt.h:58-207) + sensor pose + motion model."""
+
+    _fields_ = [
+        ("resolution", C.c_double), ("map_size_x", C.c_double), ("map_size_y", C.c_double), ("map_size_z", C.c_double),
+        ("sensor_range", C.c_double), ("max_translation_norm", C.c_double), ("max_rotation_norm", C.c_double),
+        ("delta_score", C.c_double), ("neighbours", C.c_int32), ("itr_max", C.c_int32), ("step_control", C.c_int32),
+        ("global_transf", C.c_int32), ("use_soft_constraints", C.c_int32), ("use_tikhonov", C.c_int32),
+        ("compute_cov", C.c_int32), ("fusion2d", C.c_int32), ("all_matches_valid", C.c_int32),
+        ("fuse_incomplete", C.c_int32), ("check_consistency", C.c_int32), ("force_odom_as_est", C.c_int32),
+        ("sensor_pose", C.c_double * 16), ("motion", C.c_double * 6),
+    ]
+
+
 RESULT_DTYPE = np.dtype(
     [("T", "<f8", 16), ("score", "<f8"), ("score_best", "<f8"), ("converged", "<i4"), ("iterations", "<i4"),
      ("n_hess_passes", "<i4"), ("n_grad_passes", "<i4"), ("pose_changed", "<i4"), ("exit_code", "<i4"),
@@ -142,6 +156,22 @@ def load_library():
         "ndtb_map_write_jff": (C.c_int, [vp, C.c_char_p]),
         "ndtb_map_load_jff": (C.c_int, [vp, C.c_char_p]),
         "ndtb_overlap_score": (C.c_int, [vp, vp, vp, vp, C.POINTER(dbl)]),
+        "ndtb_map_add_point_cloud": (C.c_int, [vp, vp, vp, i64, C.c_int, dbl, dbl, dbl, dbl]),
+        "ndtb_transform_point_cloud": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, C.c_int]),
+        "ndtb_fuser_default_params": (None, [C.POINTER(FuserParams)]),
+        "ndtb_fuser_create": (C.c_int, [vp, C.POINTER(FuserParams), C.POINTER(vp)]),
+        "ndtb_fuser_destroy": (None, [vp]),
+        "ndtb_fuser_initialize": (C.c_int, [vp, vp, vp, i64, C.c_int]),
+        "ndtb_fuser_update": (C.c_int, [vp, vp, vp, i64, C.c_int, C.c_int, vp, PR, vp]),
+        "ndtb_fuser_map": (vp, [vp]),
+        "ndtb_fuser_pose": (C.c_int, [vp, vp]),
+        "ndtb_graph_create": (C.c_int, [vp, C.POINTER(FuserParams), dbl, C.POINTER(vp)]),
+        "ndtb_graph_destroy": (None, [vp]),
+        "ndtb_graph_set_new_node_dist": (C.c_int, [vp, dbl]),
+        "ndtb_graph_initialize": (C.c_int, [vp, vp, vp, i64, C.c_int]),
+        "ndtb_graph_update": (C.c_int, [vp, vp, vp, i64, C.c_int, vp]),
+        "ndtb_graph_num_nodes": (i64, [vp]),
+        "ndtb_graph_node": (C.c_int, [vp, i64, vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_int32)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -314,8 +344,12 @@ class LazyGrid:
 class NDTMap:
     """lslgeneric::NDTMap(new LazyGrid(res)) resident in HBM."""
 
-    def __init__(self, engine, index=0.5):
+    def __init__(self, engine, index=0.5, borrowed_handle=None):
         self.e = engine
+        self.owned = borrowed_handle is None
+        if borrowed_handle is not None:  # a map owned by a fuser / graph node
+            self.h = C.c_void_p(borrowed_handle)
+            return
         cell = index.cell if isinstance(index, LazyGrid) else LazyGrid(index).cell
         h = C.c_void_p()
         engine.check(engine.L.ndtb_map_create(engine.h, *cell, C.byref(h)))
@@ -323,11 +357,19 @@ class NDTMap:
 
     def __del__(self):
         try:
-            if getattr(self, "h", None) and getattr(self.e, "h", None):
+            if self.owned and getattr(self, "h", None) and getattr(self.e, "h", None):
                 self.e.L.ndtb_map_destroy(self.h)
             self.h = None
         except Exception:
             pass
+
+    def addPointCloudTraced(self, origin, pts, classifierTh=0.06, maxz=100.0, sensor_noise=0.25, occupancy_limit=255.0):
+        """NDTMap::addPointCloud(origin, pc, classifierTh, maxz, sensor_noise, occupancy_limit) with the free-space ray
+        trace (ndt_feature_fuser_hmt.cpp:92,485); takes effect at the next computeNDTCells."""
+        pts = _pts4(pts)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self.e.check(self.e.L.ndtb_map_add_point_cloud(self.h, o.ctypes.data, pts.ctypes.data, pts.shape[0], HOST, classifierTh,
+                                                       maxz, sensor_noise, occupancy_limit))
 
     def guessSize(self, cx, cy, cz, sx, sy, sz):
         self.e.check(self.e.L.ndtb_map_guess_size(self.h, cx, cy, cz, sx, sy, sz))

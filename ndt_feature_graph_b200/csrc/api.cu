@@ -153,6 +153,10 @@ struct ndtb_map {
   struct Chunk {
     SlabP buf;
     int n;
+    bool trace = false;  // addPointCloud with the free-space ray trace: the points are rays from `origin`
+    double origin[3] = {0, 0, 0};
+    double maxz = 100.0, sensor_noise = 0.25;
+    float occ_limit = 255.f;
   };
   std::vector<Chunk> pending;
   bool pending_load = false;  // pending points came from loadPointCloud (fresh map)
@@ -287,8 +291,10 @@ int define_grids(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::
 // Batched (load|add)PointCloud + computeNDTCells.  pts[i] are device pointers that stay valid during the call.
 // load[i]: 1 = loadPointCloud semantics (grid (re)defined, map emptied), 2 = fresh map on the grid it already has,
 //          0 = addPointCloud (merge into the existing cells).
+using TraceSegs = std::vector<TraceSeg>;
 int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::vector<PointSrc> &pts,
-                const std::vector<char> &load, const std::vector<double> &range, uint32_t maxnumpoints, float occ_limit) {
+                const std::vector<char> &load, const std::vector<double> &range, uint32_t maxnumpoints, float occ_limit,
+                const std::vector<TraceSegs> *trace = nullptr) {
   const int M = (int)maps.size();
   if (M == 0) return NDTB_OK;
   cudaStream_t st = ctx->stream;
@@ -296,6 +302,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
   std::vector<BuildJob> jobs(M);
   std::memset(jobs.data(), 0, sizeof(BuildJob) * M);
   int max_pts = 1;
+  bool any_trace = false;
   for (int i = 0; i < M; i++) {
     jobs[i].pts = pts[i].dev;
     jobs[i].npts = pts[i].n;
@@ -304,6 +311,12 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     jobs[i].occ_limit = occ_limit;
     jobs[i].log_occ = std::log(0.6 / (1.0 - 0.6));
     max_pts = std::max(max_pts, pts[i].n);
+    if (trace && !(*trace)[i].empty()) {
+      if ((*trace)[i].size() > (size_t)MAX_TRACE_SEG) return NDTB_ERR_ARG;
+      jobs[i].n_seg = (int)(*trace)[i].size();
+      for (int q = 0; q < jobs[i].n_seg; q++) jobs[i].seg[q] = (*trace)[i][q];
+      any_trace = true;
+    }
   }
   SlabP s_jobs;
   if (int rc = slab_alloc(ctx, sizeof(BuildJob) * M, s_jobs)) return rc;
@@ -345,14 +358,15 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
   std::vector<SlabP> keep_old;  // previous storage of merged maps stays alive until the end of the build
   Carver cb, ct;
   struct OffB {
-    size_t amask, abase, tbl, counts, ptc, seg, seg2;
+    size_t amask, abase, tbl, counts, ptc, seg, seg2, viscnt, visoff;
   };
   std::vector<OffB> ob(M);
   const size_t o_counts_all = cb.take(32 * (size_t)M);  // contiguous: one D2H copy for the whole batch
   for (int i = 0; i < M; i++) {
     if (empty[i]) continue;
     ndtb_map *m = maps[i];
-    const int64_t tb_cap = std::min<int64_t>(m->nblk, (int64_t)m->n_all + pts[i].n);
+    // touched blocks: at most one new block per point, or — with the ray trace — any block of the grid
+    const int64_t tb_cap = jobs[i].n_seg ? (int64_t)m->nblk : std::min<int64_t>(m->nblk, (int64_t)m->n_all + pts[i].n);
     ob[i].amask = cb.take(8 * (size_t)m->nblk);
     ob[i].abase = cb.take(4 * (size_t)m->nblk);
     ob[i].tbl = cb.take(4 * (size_t)std::max<int64_t>(tb_cap, 1));
@@ -360,6 +374,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     ob[i].ptc = ct.take(4 * (size_t)pts[i].n);
     ob[i].seg = ct.take(4 * (size_t)pts[i].n);
     ob[i].seg2 = ct.take(4 * (size_t)pts[i].n);
+    if (jobs[i].n_seg) ob[i].viscnt = ct.take(4 * (size_t)pts[i].n), ob[i].visoff = ct.take(4 * (size_t)pts[i].n);
   }
   SlabP s_b, s_t;
   if (int rc = slab_alloc(ctx, cb.off, s_b)) return rc;
@@ -378,6 +393,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     j.pt_cell = (int *)(s_t->p + ob[i].ptc);
     j.seg_idx = (int *)(s_t->p + ob[i].seg);
     j.seg2 = (int *)(s_t->p + ob[i].seg2);
+    if (j.n_seg) j.vis_cnt = (int *)(s_t->p + ob[i].viscnt), j.vis_off = (int *)(s_t->p + ob[i].visoff);
     if (m->n_all > 0) {  // merge: start from the cells the map already has
       j.o_amask = m->amask, j.o_abase = m->abase, j.o_cmean = m->cmean, j.o_ccov = m->ccov;
       j.o_cn = m->cn, j.o_chas = m->chas, j.o_cocc = m->cocc;
@@ -392,7 +408,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
   const int L = (int)live.size();
   if (L == 0) return NDTB_OK;
   CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
-  ctx->launches += launch_mark(d_jobs, L, max_pts, st);
+  ctx->launches += launch_mark(d_jobs, L, max_pts, any_trace, st);
   std::vector<int> cnts_all(8 * (size_t)M), cnts(8 * (size_t)L);
   CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -403,9 +419,10 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
   Carver cc, ct2;
   struct OffC {
     size_t mean, cov, n, has, occ, gcell, g2c, table, cnt, segoff, cursor, gmask, gbase, ckey;
+    size_t vkey, vray, vidx, vseg2, vcnt, vsegoff;
   };
   std::vector<OffC> oc(L);
-  int max_ntb = 1, max_cells = 1;
+  int max_ntb = 1, max_cells = 1, max_vis = 1;
   for (int l = 0; l < L; l++) {  // the hash tables first, contiguous: one memset initialises them all
     int tsize = 2;
     while (tsize < 2 * cnts[8 * l + 1]) tsize <<= 1;
@@ -423,6 +440,12 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     oc[l].occ = cc.take(4 * na), oc[l].gcell = cc.take(72 * na), oc[l].g2c = cc.take(4 * na);
     oc[l].cnt = ct2.take(4 * na), oc[l].segoff = ct2.take(4 * na), oc[l].cursor = ct2.take(4 * na), oc[l].ckey = ct2.take(4 * na);
     oc[l].gmask = ct2.take(8 * (size_t)std::max(ntb, 1)), oc[l].gbase = ct2.take(4 * (size_t)std::max(ntb, 1));
+    if (live[l].n_seg) {
+      const size_t nv = (size_t)std::max(cnts[8 * l + 7], 1);
+      max_vis = std::max(max_vis, cnts[8 * l + 7]);
+      oc[l].vkey = ct2.take(4 * nv), oc[l].vray = ct2.take(4 * nv), oc[l].vidx = ct2.take(4 * nv), oc[l].vseg2 = ct2.take(4 * nv);
+      oc[l].vcnt = ct2.take(4 * na), oc[l].vsegoff = ct2.take(4 * na);
+    }
   }
   SlabP s_c, s_t2;
   if (int rc = slab_alloc(ctx, cc.off, s_c)) return rc;
@@ -438,9 +461,28 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     j.cnt = (int *)(s_t2->p + oc[l].cnt), j.seg_off = (int *)(s_t2->p + oc[l].segoff), j.cursor = (int *)(s_t2->p + oc[l].cursor);
     j.gmask_t = (unsigned long long *)(s_t2->p + oc[l].gmask), j.gbase_t = (int *)(s_t2->p + oc[l].gbase);
     j.cell_key = (int *)(s_t2->p + oc[l].ckey);
+    if (j.n_seg) {
+      j.vis_key = (int *)(s_t2->p + oc[l].vkey), j.vis_ray = (int *)(s_t2->p + oc[l].vray);
+      j.v_cnt = (int *)(s_t2->p + oc[l].vcnt), j.v_seg_off = (int *)(s_t2->p + oc[l].vsegoff), j.v_seg2 = (int *)(s_t2->p + oc[l].vseg2);
+    }
   }
   CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
   pt.mark("alloc C");
+  SlabP s_vjobs;
+  if (any_trace) {  // per-cell visit lists through the points' counting sort: the same kernels on the per-visit arrays
+    std::vector<BuildJob> vj(live);
+    for (int l = 0; l < L; l++) {
+      BuildJob &v = vj[l];
+      v.pts = nullptr;
+      v.npts = live[l].n_seg ? cnts[8 * l + 7] : 0;
+      v.pt_cell = live[l].vis_key, v.seg_idx = live[l].n_seg ? (int *)(s_t2->p + oc[l].vidx) : nullptr, v.seg2 = live[l].v_seg2;
+      v.cnt = live[l].v_cnt, v.seg_off = live[l].v_seg_off;
+      if (!live[l].n_seg) v.n_all = 0, v.cnt = nullptr;  // nothing to do for a map without traced rays
+    }
+    if (int rc = slab_alloc(ctx, sizeof(BuildJob) * L, s_vjobs)) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(s_vjobs->p, vj.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
+    ctx->launches += launch_trace_lists(d_jobs, (const BuildJob *)s_vjobs->p, L, max_pts, max_vis, max_ntb, max_cells, st);
+  }
   ctx->launches += launch_cells(d_jobs, L, max_pts, max_ntb, max_cells, st);
   pt.mark("cells");
   ctx->launches += launch_gview(d_jobs, L, max_ntb, st);
@@ -459,7 +501,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     m->gcell = j.gcell, m->g2c = j.g2c, m->table = j.table, m->tsize = j.tsize;
   }
   pt.mark("publish");
-  s_t.reset(), s_t2.reset(), s_jobs.reset(), keep_old.clear();
+  s_t.reset(), s_t2.reset(), s_jobs.reset(), s_vjobs.reset(), keep_old.clear();
   pt.mark("free temps");
   return NDTB_OK;
 }
@@ -849,6 +891,31 @@ int ndtb_map_add_points(ndtb_map *m, const float *pts, int64_t n, int mem, int64
   return NDTB_OK;
 }
 
+int ndtb_map_add_point_cloud(ndtb_map *m, const double *origin, const float *pts, int64_t n, int mem, double classifier_th,
+                             double maxz, double sensor_noise, double occupancy_limit) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
+  (void)classifier_th;  // unused by the upstream branch restated here
+  if (!m || !origin || n < 0 || n > 0x7fffffff || (n > 0 && !pts)) return NDTB_ERR_ARG;
+  if (m->is_first_load) return ndtb_map_load_point_cloud(m, pts, n, -1.0, mem, nullptr);  // NDTMap::addPointCloud: isFirstLoad_
+  if (!m->grid_ready) return NDTB_ERR_GRID;
+  ndtb_ctx *ctx = m->ctx;
+  SlabP buf;
+  if (int rc = stage_points(ctx, pts, n, mem, buf)) return rc;
+  if (m->pending_load && m->pending_built) {
+    m->pending.clear();
+    m->pending_load = false;
+  }
+  int traced = 0;
+  for (auto &c : m->pending) traced += c.trace;
+  if (traced >= MAX_TRACE_SEG) return NDTB_ERR_ARG;
+  ndtb_map::Chunk c;
+  c.buf = buf, c.n = (int)n, c.trace = true;
+  for (int i = 0; i < 3; i++) c.origin[i] = origin[i];
+  c.maxz = maxz, c.sensor_noise = sensor_noise, c.occ_limit = (float)occupancy_limit;
+  m->pending.push_back(c);
+  return NDTB_OK;
+}
+
 int ndtb_map_compute_cells(ndtb_map *m, uint32_t maxnumpoints, float occupancy_limit) {
   DeviceGuard dev_guard(m ? m->ctx : nullptr);
   if (!m) return NDTB_ERR_ARG;
@@ -880,7 +947,20 @@ int ndtb_map_compute_cells(ndtb_map *m, uint32_t maxnumpoints, float occupancy_l
   const char load = m->pending_load ? 2 : 0;
   std::vector<ndtb_map *> maps{m};
   std::vector<PointSrc> ps{{ptr, (int)total}};
-  const int rc = build_batch(ctx, maps, ps, {load}, {m->pending_range}, maxnumpoints, occupancy_limit);
+  std::vector<TraceSegs> segs(1);
+  {
+    int at = 0;
+    for (auto &c : m->pending) {
+      if (c.trace) {
+        TraceSeg sg;
+        for (int i = 0; i < 3; i++) sg.origin[i] = c.origin[i];
+        sg.maxz = c.maxz, sg.sensor_noise = c.sensor_noise, sg.occ_limit = c.occ_limit, sg.begin = at, sg.end = at + c.n;
+        segs[0].push_back(sg);
+      }
+      at += c.n;
+    }
+  }
+  const int rc = build_batch(ctx, maps, ps, {load}, {m->pending_range}, maxnumpoints, occupancy_limit, &segs);
   m->pending.clear();
   m->pending_load = false;
   return rc;
@@ -1332,6 +1412,59 @@ int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, 
   ctx->launches += launch_overlap((const BuildJob *)(s->p + o_j), (const double *)(s->p + o_T), (double *)(s->p + o_out), ctx->stream);
   CU_TRY(ctx, cudaMemcpyAsync(score, s->p + o_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NDTB_OK;
+}
+
+int ndtb_transform_point_cloud(ndtb_ctx *ctx, const double *T16, const float *in, int64_t n, int in_mem, float *out, int out_mem) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !T16 || n < 0 || n > 0x7fffffff || (n > 0 && (!in || !out))) return NDTB_ERR_ARG;
+  if (n == 0) return NDTB_OK;
+  cudaStream_t st = ctx->stream;
+  SlabP ibuf, obuf, tbuf;
+  const float4 *d_in = (const float4 *)in;
+  if (in_mem != NDTB_MEM_DEVICE) {
+    if (int rc = stage_points(ctx, in, n, in_mem, ibuf)) return rc;
+    d_in = (const float4 *)ibuf->p;
+  }
+  float4 *d_out = (float4 *)out;
+  if (out_mem != NDTB_MEM_DEVICE) {
+    if (int rc = slab_alloc(ctx, 16 * (size_t)n, obuf)) return rc;
+    d_out = (float4 *)obuf->p;
+  }
+  float T12[12];  // Eigen::Affine3d::cast<float>(): every coefficient rounded to float
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) T12[r * 3 + c] = (float)T16[c * 4 + r];
+    T12[9 + r] = (float)T16[12 + r];
+  }
+  if (int rc = slab_alloc(ctx, sizeof T12, tbuf)) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(tbuf->p, T12, sizeof T12, cudaMemcpyHostToDevice, st));
+  ctx->launches += launch_transform_points(d_in, d_out, (int)n, (const float *)tbuf->p, st);
+  if (out_mem != NDTB_MEM_DEVICE) {
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 16 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+  } else {
+    CU_TRY(ctx, cudaStreamSynchronize(st));  // T12 is a stack array: the copy must have been consumed before returning
+  }
+  return NDTB_OK;
+}
+
+// device scratch for the front end (fuser.cu): a stream-ordered buffer owned by the context's pool
+int ndtb_internal_alloc(ndtb_ctx *ctx, size_t bytes, void **out) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !out) return NDTB_ERR_ARG;
+  CU_TRY(ctx, cudaMallocFromPoolAsync(out, bytes ? bytes : 256, ctx->pool, ctx->stream));
+  return NDTB_OK;
+}
+void ndtb_internal_free(ndtb_ctx *ctx, void *p) {
+  DeviceGuard dev_guard(ctx);
+  if (ctx && p) cudaFreeAsync(p, ctx->stream);
+}
+int ndtb_internal_upload(ndtb_ctx *ctx, void *dst, const void *src, size_t bytes, int src_mem) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx) return NDTB_ERR_ARG;
+  CU_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, src_mem == NDTB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                              ctx->stream));
+  if (src_mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may reuse its buffer
   return NDTB_OK;
 }
 

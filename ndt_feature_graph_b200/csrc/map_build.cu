@@ -201,6 +201,110 @@ __global__ void k_extent(const BuildJob *__restrict__ jobs, const int *__restric
   }
 }
 
+__device__ __forceinline__ int cta_excl_scan(int v, int *tot, int *wsum);
+
+// ---- free-space ray trace (NDTMap::addPointCloud + LazyGrid::traceLine [upstream]) ---------------------------
+// call sites ndt_feature_fuser_hmt.cpp:92 (initialize) and :485 (update).  A pending point that belongs to a trace
+// segment is a ray from the segment's origin: the ray is dropped (end point included) when it is longer than 200 m or
+// ends above maxz; otherwise N = int(l / min cell size) and the N-2 samples origin + (i+1) diff/N, rounded to FLOAT
+// points, are looked up with the LazyGrid index rule; a sample in the voxel of the previous sample is skipped.
+__device__ __forceinline__ int seg_of(const BuildJob &j, int i) {
+  for (int s = 0; s < j.n_seg; s++)
+    if (i >= j.seg[s].begin && i < j.seg[s].end) return s;
+  return -1;
+}
+// false: the ray (and its end point) is ignored
+__device__ __forceinline__ bool ray_setup(const BuildJob &j, const TraceSeg &sg, const float4 p, double *d, int &N, double &l) {
+  if (isnan(p.x) || isnan(p.y) || isnan(p.z)) return false;
+  const double f0 = (double)p.x - sg.origin[0], f1 = (double)p.y - sg.origin[1], f2 = (double)p.z - sg.origin[2];
+  l = sqrt(f0 * f0 + f1 * f1 + f2 * f2);
+  if (l > 200.) return false;
+  if ((double)p.z > sg.maxz) return false;
+  const double m1 = j.g.cell[0] < j.g.cell[1] ? j.g.cell[0] : j.g.cell[1];
+  const double m2 = j.g.cell[2] < j.g.cell[1] ? j.g.cell[2] : j.g.cell[1];
+  const double res = m1 < m2 ? m1 : m2;
+  if (res < 0.01) return false;
+  N = __double2int_rz(l / res);
+  const double fN = (double)(float)N;
+  d[0] = f0 / fN, d[1] = f1 / fN, d[2] = f2 / fN;
+  return true;
+}
+// calls visit(key) for every cell the ray meets, in order
+template <class F>
+__device__ __forceinline__ void ray_walk(const BuildJob &j, const TraceSeg &sg, const double *d, int N, F visit) {
+  int xo = 0, yo = 0, zo = 0;
+  for (int s = 0; s < N - 2; s++) {
+    const double f = (double)(float)(s + 1);
+    const float qx = (float)(sg.origin[0] + f * d[0]), qy = (float)(sg.origin[1] + f * d[1]), qz = (float)(sg.origin[2] + f * d[2]);
+    int x, y, z;
+    if (!voxel_index(j.g, (double)qx, (double)qy, (double)qz, x, y, z)) continue;
+    if (x == xo && y == yo && z == zo) continue;
+    xo = x, yo = y, zo = z;
+    if (!in_grid(j.g, x, y, z)) continue;
+    visit(block_id(j.g, x, y, z) * 64 + block_bit(x, y, z));
+  }
+}
+
+// thread per ray: mark the voxels it meets (they become cells) and count them
+__global__ void k_trace_count(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  if (j.n_seg == 0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
+    int cnt = 0;
+    const int s = seg_of(j, i);
+    if (s >= 0) {
+      double d[3], l;
+      int N;
+      if (ray_setup(j, j.seg[s], j.pts[i], d, N, l))
+        ray_walk(j, j.seg[s], d, N, [&](int key) {
+          const unsigned long long bit = 1ull << (key & 63);
+          if (!(__ldcg(j.amask + (key >> 6)) & bit)) atomicOr(j.amask + (key >> 6), bit);
+          cnt++;
+        });
+    }
+    j.vis_cnt[i] = cnt;
+  }
+}
+
+// one CTA per map: exclusive scan of the per-ray visit counts
+__global__ void __launch_bounds__(1024) k_rayscan(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.x];
+  if (j.n_seg == 0) {
+    if (threadIdx.x == 0) j.counts[7] = 0;
+    return;
+  }
+  __shared__ int wsum[32];
+  int run = 0;
+  for (int base = 0; base < j.npts; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < j.npts ? j.vis_cnt[i] : 0;
+    int t;
+    const int e = cta_excl_scan(v, &t, wsum);
+    if (i < j.npts) j.vis_off[i] = run + e;
+    run += t;
+  }
+  if (threadIdx.x == 0) j.counts[7] = run;
+}
+
+// thread per ray: the same walk again, writing (voxel key, ray) of every visit at its ray-major position
+__global__ void k_trace_fill(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  if (j.n_seg == 0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
+    if (j.vis_cnt[i] == 0) continue;
+    const int s = seg_of(j, i);
+    double d[3], l;
+    int N;
+    if (!ray_setup(j, j.seg[s], j.pts[i], d, N, l)) continue;
+    int at = j.vis_off[i];
+    ray_walk(j, j.seg[s], d, N, [&](int key) {
+      j.vis_key[at] = key;
+      j.vis_ray[at] = i;
+      at++;
+    });
+  }
+}
+
 // ---- binning -----------------------------------------------------------------------------------------
 // Four points per thread and iteration, all loads of a stage issued before the first use: the kernel is bound by the
 // latency of the dependent mask look-up, not by bytes.
@@ -219,8 +323,16 @@ __global__ void k_mark(const BuildJob *__restrict__ jobs) {
     for (int u = 0; u < 4; u++) {
       int ix, iy, iz;
       key[u] = -1, b[u] = 0, bit[u] = 0;
-      if (!pt_skip(p[u], j.range_limit) && voxel_index(j.g, (double)p[u].x, (double)p[u].y, (double)p[u].z, ix, iy, iz) &&
-          in_grid(j.g, ix, iy, iz)) {
+      bool live = !pt_skip(p[u], j.range_limit);
+      if (live && j.n_seg) {  // the end point of a ray that addPointCloud ignores is not binned either
+        const int sgi = seg_of(j, i0 + u * stride);
+        if (sgi >= 0) {
+          double dd[3], l;
+          int N;
+          live = ray_setup(j, j.seg[sgi], p[u], dd, N, l);
+        }
+      }
+      if (live && voxel_index(j.g, (double)p[u].x, (double)p[u].y, (double)p[u].z, ix, iy, iz) && in_grid(j.g, ix, iy, iz)) {
         b[u] = block_id(j.g, ix, iy, iz), bit[u] = block_bit(ix, iy, iz);
         key[u] = b[u] * 64 + bit[u];
       }
@@ -428,7 +540,7 @@ __global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restric
   const BuildJob &j = jobs[blockIdx.y];
   const int lane = threadIdx.x & 31;
   int *sb = sbuf[threadIdx.x >> 5];
-  const int ntb = j.counts[1];
+  const int ntb = j.cnt ? j.counts[1] : 0;  // a map without visit lists in a ray-traced batch has no per-visit arrays
   const int bits = 32 - __clz(j.npts > 1 ? j.npts - 1 : 1);
   for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ntb; t += gridDim.x * 8) {
     const int b = j.tb_list[t];
@@ -479,6 +591,115 @@ __global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restric
   }
 }
 
+// Occupancy evidence of one traced ray for a cell that holds a Gaussian (NDTMap::addPointCloud [upstream], REFACTORED
+// branch): maximum-likelihood point X of the cell's Gaussian on the line (NDTCell::computeMaximumLikelihoodAlongLine,
+// origin rounded to float like pcl::PointXYZ po), its likelihood (getLikelihood of the float-rounded X), damped by the
+// probability that X is the end point itself.  Returns false when the ray leaves the cell untouched.
+__device__ __forceinline__ bool inv3_cofactor(const double *m, double *inv) {  // Eigen computeInverseAndDetWithCheck order
+  const double c00 = m[4] * m[8] - m[5] * m[7];
+  const double c10 = m[2] * m[7] - m[1] * m[8];
+  const double c20 = m[1] * m[5] - m[2] * m[4];
+  const double det = c00 * m[0] + c10 * m[3] + c20 * m[6];
+  if (!(fabs(det) > 1e-12)) return false;
+  const double id = 1.0 / det;
+  inv[0] = c00 * id, inv[1] = c10 * id, inv[2] = c20 * id;
+  inv[3] = (m[5] * m[6] - m[3] * m[8]) * id;
+  inv[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+  inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  inv[6] = (m[3] * m[7] - m[4] * m[6]) * id;
+  inv[7] = (m[1] * m[6] - m[0] * m[7]) * id;
+  inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return true;
+}
+__device__ bool ray_gaussian_evidence(const double *mean, const double *icov, bool icov_ok, const TraceSeg &sg, const float4 p,
+                                      float &logodd_out) {
+  const double po[3] = {(double)(float)sg.origin[0], (double)(float)sg.origin[1], (double)(float)sg.origin[2]};
+  const double pe[3] = {(double)p.x, (double)p.y, (double)p.z};
+  const double f0 = pe[0] - sg.origin[0], f1 = pe[1] - sg.origin[1], f2 = pe[2] - sg.origin[2];
+  const double l = sqrt(f0 * f0 + f1 * f1 + f2 * f2);
+  double X[3] = {pe[0], pe[1], pe[2]};
+  double lik = 1.0;
+  if (icov_ok) {
+    double L[3] = {pe[0] - po[0], pe[1] - po[1], pe[2] - po[2]};
+    const double nrm = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    L[0] /= nrm, L[1] /= nrm, L[2] /= nrm;
+    const double A[3] = {icov[0] * L[0] + icov[1] * L[1] + icov[2] * L[2], icov[3] * L[0] + icov[4] * L[1] + icov[5] * L[2],
+                         icov[6] * L[0] + icov[7] * L[1] + icov[8] * L[2]};
+    const double B[3] = {pe[0] - mean[0], pe[1] - mean[1], pe[2] - mean[2]};
+    const double sigma = A[0] * L[0] + A[1] * L[1] + A[2] * L[2];
+    if (sigma != 0) {
+      const double t = -(A[0] * B[0] + A[1] * B[1] + A[2] * B[2]) / sigma;
+      X[0] = L[0] * t + pe[0], X[1] = L[1] * t + pe[1], X[2] = L[2] * t + pe[2];
+      const double v[3] = {(double)(float)X[0] - mean[0], (double)(float)X[1] - mean[1], (double)(float)X[2] - mean[2]};
+      const double iv[3] = {icov[0] * v[0] + icov[1] * v[1] + icov[2] * v[2], icov[3] * v[0] + icov[4] * v[1] + icov[5] * v[2],
+                            icov[6] * v[0] + icov[7] * v[1] + icov[8] * v[2]};
+      const double q = v[0] * iv[0] + v[1] * iv[1] + v[2] * iv[2];
+      lik = isnan(q) ? -1.0 : exp(-q / 2);
+    }
+  }
+  const double dist = sqrt((sg.origin[0] - X[0]) * (sg.origin[0] - X[0]) + (sg.origin[1] - X[1]) * (sg.origin[1] - X[1]) +
+                           (sg.origin[2] - X[2]) * (sg.origin[2] - X[2]));
+  if (dist > l) return false;
+  const double l2 = sqrt((X[0] - pe[0]) * (X[0] - pe[0]) + (X[1] - pe[1]) * (X[1] - pe[1]) + (X[2] - pe[2]) * (X[2] - pe[2]));
+  const double snoise = 0.5 * (dist / 30.0) + sg.sensor_noise;
+  const double thr = exp(-0.5 * (l2 * l2) / (snoise * snoise));
+  lik *= (1.0 - thr);
+  if (lik < 0.3) return false;
+  lik = 0.1 * lik + 0.5;
+  logodd_out = (float)log((1.0 - lik) / lik);
+  return true;
+}
+
+// (a') ray-traced builds only, one thread per cell: the free-space evidence of the rays that met the cell, applied to
+// its stored occupancy in the order the rays were traced; a cell whose occupancy drops to <= 0 loses its Gaussian at
+// once (later rays of the same scan see an empty cell).  Leaves (occupancy, hasGaussian) in the new record for k_cells.
+__global__ void __launch_bounds__(128) k_cell_trace(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  if (j.n_seg == 0) return;
+  const float4 *__restrict__ pts = j.pts;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < j.n_all; c += gridDim.x * blockDim.x) {
+    const int key = j.cell_key[c];
+    const int b = key >> 6, bit = key & 63;
+    double mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int has = 0;
+    float occ = 0.f;
+    if (j.o_amask) {
+      const unsigned long long om = j.o_amask[b];
+      if (om >> bit & 1ull) {
+        const int oc = j.o_abase[b] + __popcll(om & ((1ull << bit) - 1ull));
+        has = j.o_chas[oc], occ = j.o_cocc[oc];
+        if (has) {
+          for (int q = 0; q < 3; q++) mean[q] = j.o_cmean[(size_t)oc * 3 + q];
+          for (int q = 0; q < 9; q++) cov[q] = j.o_ccov[(size_t)oc * 9 + q];
+        }
+      }
+    }
+    {
+      const int nv = j.v_cnt[c];
+      const int *__restrict__ vids = j.v_seg2 + j.v_seg_off[c];
+      double icov[9];
+      bool icov_ok = false, icov_done = false;
+      for (int q = 0; q < nv; q++) {
+        const int ray = j.vis_ray[vids[q]];
+        const TraceSeg &sg = j.seg[seg_of(j, ray)];
+        float ev = (float)-0.2;
+        bool apply = true;
+        if (has) {
+          if (!icov_done) icov_ok = inv3_cofactor(cov, icov), icov_done = true;
+          apply = ray_gaussian_evidence(mean, icov, icov_ok, sg, pts[ray], ev);
+        }
+        if (apply) {
+          occ += ev;
+          occ = occ > sg.occ_limit ? sg.occ_limit : occ;
+          occ = occ < -sg.occ_limit ? -sg.occ_limit : occ;
+          if (occ <= 0.f) has = 0;
+        }
+      }
+    }
+    j.cocc[c] = occ, j.chas[c] = has;
+  }
+}
+
 // (b) one THREAD per cell: sequential mean and scatter matrix over its points in id order (the operation order of
 // NDTCell::computeGaussian), merge with the stored (N, mean, cov), occupancy.  Cells whose covariance has to go through
 // rescaleCovariance are appended to the map's eigen list (the dead `cursor` array) and finished by k_eigen: the 3x3
@@ -504,16 +725,20 @@ __global__ void __launch_bounds__(128, NDTB_KCELLS_MINBLOCKS) k_cells(const Buil
         N = j.o_cn[oc], has = j.o_chas[oc], occ = j.o_cocc[oc];
       }
     }
+    if (j.n_seg) occ = j.cocc[c], has = j.chas[c];  // occupancy / Gaussian flag after the ray trace (k_cell_trace)
     const int n = j.cnt[c];
     bool eigen = false;
-    if (n > 0) {
+    bool emptied = false;
+    if (n > 0) {  // occupancy: += n*log(0.6/0.4), clamped (NDTCell::updateOccupancy); a cell whose occupancy is still <= 0
+                  // (free-space evidence outweighs the hits) loses its Gaussian and drops the points [upstream computeGaussian]
+      float o2 = occ + (float)((double)n * j.log_occ);
+      o2 = o2 > j.occ_limit ? j.occ_limit : o2;
+      o2 = o2 < -j.occ_limit ? -j.occ_limit : o2;
+      occ = o2;
+      if (occ <= 0.f) has = 0, emptied = true;
+    }
+    if (n > 0 && !emptied) {
       const int *__restrict__ ids = j.seg2 + j.seg_off[c];
-      {  // occupancy: += n*log(0.6/0.4), clamped (NDTCell::updateOccupancy)
-        float o2 = occ + (float)((double)n * j.log_occ);
-        o2 = o2 > j.occ_limit ? j.occ_limit : o2;
-        o2 = o2 < -j.occ_limit ? -j.occ_limit : o2;
-        occ = o2;
-      }
       if (has || n >= 3) {
         // the additions stay in id order; the gathers of four points are issued together
         double ms0 = 0, ms1 = 0, ms2 = 0;
@@ -814,6 +1039,23 @@ __global__ void __launch_bounds__(256) k_overlap(const BuildJob *__restrict__ jo
   }
 }
 
+// lslgeneric::transformPointCloudInPlace [upstream]: the pose is cast to FLOAT and applied in float, column by column
+// (Eigen's 3x3 matrix * vector accumulates col0*x + col1*y + col2*z), then the translation is added.  T12 = R row-major, t.
+__global__ void k_transform_points(const float4 *__restrict__ in, float4 *__restrict__ out, int n, const float *__restrict__ T12) {
+  float T[12];
+#pragma unroll
+  for (int q = 0; q < 12; q++) T[q] = T12[q];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = in[i];
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], p.x), __fmul_rn(T[1], p.y)), __fmul_rn(T[2], p.z)), T[9]);
+    o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[3], p.x), __fmul_rn(T[4], p.y)), __fmul_rn(T[5], p.z)), T[10]);
+    o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[6], p.x), __fmul_rn(T[7], p.y)), __fmul_rn(T[8], p.z)), T[11]);
+    o.w = p.w;
+    out[i] = o;
+  }
+}
+
 // ---- launch wrappers (host) ---------------------------------------------------------------------------
 static inline int chunks_for(int n, int per) {
   int c = (n + per - 1) / per;
@@ -830,10 +1072,30 @@ int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int ma
   k_extent<<<dim3(chunks_for(max_pts, 1024), n_which), 256, 0, s>>>(d_jobs, d_which, d_out);
   return 3;
 }
-int launch_mark(const BuildJob *d_jobs, int n, int max_pts, cudaStream_t s) {
+int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, cudaStream_t s) {
   k_mark<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
+  if (trace) {
+    k_trace_count<<<dim3(chunks_for(max_pts, 128), n), 128, 0, s>>>(d_jobs);
+    k_rayscan<<<n, 1024, 0, s>>>(d_jobs);
+  }
   k_blockscan<<<n, 1024, 0, s>>>(d_jobs);
-  return 2;
+  return trace ? 4 : 2;
+}
+// per-cell visit lists: fill the ray-major visit arrays, then the counting sort the points go through (d_vjobs: npts =
+// number of visits, pt_cell = vis_key, cnt / seg_off / seg_idx / seg2 = the visit arrays)
+int launch_trace_lists(const BuildJob *d_jobs, const BuildJob *d_vjobs, int n, int max_pts, int max_vis, int max_ntb, int max_cells,
+                       cudaStream_t s) {
+  k_trace_fill<<<dim3(chunks_for(max_pts, 128), n), 128, 0, s>>>(d_jobs);
+  k_count<<<dim3(chunks_for(max_vis, 1024), n), 256, 0, s>>>(d_vjobs);
+  k_segscan<<<n, 1024, 0, s>>>(d_vjobs);
+  k_scatter<<<dim3(chunks_for(max_vis, 1024), n), 256, 0, s>>>(d_vjobs);
+  k_sort_segments<<<dim3(chunks_for(max_ntb, 8), n), 256, 0, s>>>(d_vjobs);
+  k_cell_trace<<<dim3(chunks_for(max_cells, 128), n), 128, 0, s>>>(d_jobs);
+  return 6;
+}
+int launch_transform_points(const float4 *d_in, float4 *d_out, int n, const float *d_T12, cudaStream_t s) {
+  k_transform_points<<<chunks_for(n, 1024), 256, 0, s>>>(d_in, d_out, n, d_T12);
+  return 1;
 }
 int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int max_cells, cudaStream_t s) {
   k_count<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);

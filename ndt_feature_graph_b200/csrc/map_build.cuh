@@ -6,6 +6,14 @@
 
 namespace ndtb {
 
+constexpr int MAX_TRACE_SEG = 4;  // addPointCloud calls (each with its own origin) between two computeNDTCells calls
+struct TraceSeg {
+  double origin[3];
+  double maxz, sensor_noise;
+  float occ_limit;
+  int begin, end;  // range of pending points traced from this origin
+};
+
 // One map of a batched build.  Pointers address this map's slice of the batch slabs.
 struct BuildJob {
   GridDesc g;
@@ -46,6 +54,16 @@ struct BuildJob {
   unsigned maxnumpoints;
   float occ_limit;
   double log_occ;  // log(0.6/0.4) evaluated on the host
+  // ---- free-space ray trace of NDTMap::addPointCloud (LazyGrid::traceLine): the pending points [begin, end) of a
+  // segment are rays from that segment's origin.  n_seg == 0: plain end-point binning.
+  int n_seg;
+  TraceSeg seg[MAX_TRACE_SEG];
+  int *vis_cnt;   // [npts] cells met by ray i (deduplicated, inside the grid)
+  int *vis_off;   // [npts] exclusive scan of vis_cnt; total in counts[7]
+  int *vis_key;   // [n_vis] voxel key (block*64+bit) of visit v, then the cell id; visits are numbered ray-major
+  int *vis_ray;   // [n_vis] ray (= point index) of visit v
+  int *v_cnt, *v_seg_off;  // [n_all] visits per cell, segment offsets
+  int *v_seg2;    // [n_vis] visit ids grouped by cell, ascending inside a cell (= the order the rays were traced in)
 };
 
 int centroid_chunk_points();
@@ -54,7 +72,11 @@ int centroid_record_doubles();
 // centroid_chunk_points() points)
 int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, const long long *d_rec_off, double *d_recs,
                  double *d_out, cudaStream_t s);
-int launch_mark(const BuildJob *d_jobs, int n, int max_pts, cudaStream_t s);
+int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, cudaStream_t s);
+// visit lists of the ray trace: d_vjobs = the jobs with the per-point arrays replaced by the per-visit arrays
+int launch_trace_lists(const BuildJob *d_jobs, const BuildJob *d_vjobs, int n, int max_pts, int max_vis, int max_ntb, int max_cells,
+                       cudaStream_t s);
+int launch_transform_points(const float4 *d_in, float4 *d_out, int n, const float *d_T12, cudaStream_t s);
 int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int max_cells, cudaStream_t s);
 int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s);
 int launch_blockscan(const BuildJob *d_jobs, int n, cudaStream_t s);

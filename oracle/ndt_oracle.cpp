@@ -407,6 +407,14 @@ void compute_gaussian(Cell &c, uint32_t maxnumpoints, float occupancy_limit) {
     if (occ < -occupancy_limit) occ = -occupancy_limit;
     c.occ = occ;
   }
+  // [upstream] after the occupancy update: if(occ<=0){ hasGaussian_=false; return; } -- the cell keeps its old
+  // (N, mean, cov) and computeNDTCells moves its leftover points_ to conflictPoints.  Only reachable after the
+  // free-space ray trace of addPointCloud has driven the occupancy negative.
+  if (c.occ <= 0.f) {
+    c.has_gaussian = false;
+    c.pts.clear();
+    return;
+  }
   if ((!c.has_gaussian && n < 3) || n == 0) {
     c.pts.clear();
     return;
@@ -1224,6 +1232,115 @@ int64_t orc_map_add_points(orc_map *m, const float *pts, int64_t n) {
   int64_t added = 0;
   for (int64_t i = 0; i < n; i++)
     if (m->add_point(pts + 4 * i)) added++;
+  return added;
+}
+
+// NDTMap::addPointCloud(origin, pc, classifierTh, maxz, sensor_noise, occupancy_limit) [upstream, REFACTORED branch]
+// with LazyGrid::traceLine: the free-space ray trace + occupancy update the fuser runs on the node map
+// (call sites ndt_feature_fuser_hmt.cpp:92 and :485).  Per point, in cloud order:
+//   diff = p - origin, l = |diff| (skip NaN points and l > 200 m);
+//   traceLine: skip the ray if p.z > maxz; N = int(l / min cell size); N-2 samples origin + (i+1) diff/N, stored as
+//   FLOAT points, voxel index by the LazyGrid rule; a sample in the same voxel as the previous one is skipped, out of
+//   grid samples are skipped;
+//   every cell met:  no Gaussian -> occupancy -= 0.2;  Gaussian -> maximum-likelihood point X of the cell's Gaussian on
+//   the line (NDTCell::computeMaximumLikelihoodAlongLine), lik = exp(-d_M(X)^2/2); ignored when X lies beyond the end
+//   point; lik *= 1 - exp(-|X-p|^2 / (2 (0.5 dist/30 + sensor_noise)^2)); ignored when < 0.3; occupancy +=
+//   log((1-q)/q), q = 0.1 lik + 0.5;  occupancy clamped to +-limit, and a cell whose occupancy drops to <= 0 loses its
+//   Gaussian at once (later rays of the same scan see it as an empty cell);
+//   finally the end point is binned like loadPointCloud does (LazyGrid::addPoint, update_set).
+// `classifierTh` is unused by this branch upstream.  The cells of an initialize()d map all exist ("initializeAll"); for
+// a lazily allocated grid upstream would add the sample as a fake point to the new cell — here (and in the engine) a
+// cell met by a ray on such a map is simply created empty, documented deviation outside the reference's call sites.
+namespace {
+inline double cell_line_likelihood(const Cell &c, const double *po /*float-rounded origin*/, const double *pe, double *X) {
+  double L[3] = {pe[0] - po[0], pe[1] - po[1], pe[2] - po[2]};
+  const double nrm = std::sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+  for (int a = 0; a < 3; a++) L[a] /= nrm;
+  double icov[9], det;
+  if (!inv3_check(c.cov, icov, det)) {  // icov_ undefined upstream in that case; treat like sigma == 0
+    for (int a = 0; a < 3; a++) X[a] = pe[a];
+    return 1.0;
+  }
+  double A[3];
+  mat3_vec(icov, L, A);
+  const double B[3] = {pe[0] - c.mean[0], pe[1] - c.mean[1], pe[2] - c.mean[2]};
+  const double sigma = A[0] * L[0] + A[1] * L[1] + A[2] * L[2];
+  if (sigma == 0) {
+    for (int a = 0; a < 3; a++) X[a] = pe[a];  // `out` is left untouched upstream; the caller's value is unspecified
+    return 1.0;
+  }
+  const double t = -(A[0] * B[0] + A[1] * B[1] + A[2] * B[2]) / sigma;
+  for (int a = 0; a < 3; a++) X[a] = L[a] * t + pe[a];
+  // getLikelihood(pcl::PointXYZ): the point is rounded to float
+  const double v[3] = {(double)(float)X[0] - c.mean[0], (double)(float)X[1] - c.mean[1], (double)(float)X[2] - c.mean[2]};
+  double iv[3];
+  mat3_vec(icov, v, iv);
+  const double lik = v[0] * iv[0] + v[1] * iv[1] + v[2] * iv[2];
+  if (std::isnan(lik)) return -1;
+  return std::exp(-lik / 2);
+}
+inline void update_occupancy(Cell &c, float v, float limit) {  // NDTCell::updateOccupancy
+  c.occ += v;
+  if (c.occ > limit) c.occ = limit;
+  if (c.occ < -limit) c.occ = -limit;
+}
+}  // namespace
+
+int64_t orc_map_add_point_cloud(orc_map *m, const double *origin, const float *pts, int64_t n, double classifier_th,
+                                double maxz, double sensor_noise, double occupancy_limit) {
+  (void)classifier_th;
+  if (m->is_first_load) return orc_map_load_point_cloud(m, pts, n, -1.0);
+  if (!m->grid_ready) return -1;
+  const double po[3] = {(double)(float)origin[0], (double)(float)origin[1], (double)(float)origin[2]};
+  const double max_range = 200.;
+  const double resolution = std::min(std::min(m->cell[0], m->cell[1]), std::min(m->cell[2], m->cell[1]));
+  int64_t added = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const float *p = pts + 4 * i;
+    if (std::isnan(p[0]) || std::isnan(p[1]) || std::isnan(p[2])) continue;
+    const double pe[3] = {p[0], p[1], p[2]};
+    const double diff[3] = {pe[0] - origin[0], pe[1] - origin[1], pe[2] - origin[2]};
+    const double l = std::sqrt(diff[0] * diff[0] + diff[1] * diff[1] + diff[2] * diff[2]);
+    if (l > max_range) continue;
+    // ---- LazyGrid::traceLine
+    if (pe[2] > maxz) continue;
+    if (resolution < 0.01) continue;
+    const int N = (int)(l / resolution);
+    const double fN = (double)(float)N;
+    const double d[3] = {diff[0] / fN, diff[1] / fN, diff[2] / fN};
+    int xo = 0, yo = 0, zo = 0;
+    for (int s = 0; s < N - 2; s++) {
+      const double f = (double)(float)(s + 1);
+      const float q[3] = {(float)(origin[0] + f * d[0]), (float)(origin[1] + f * d[1]), (float)(origin[2] + f * d[2])};
+      int x, y, z;
+      if (!m->index_of(q[0], q[1], q[2], x, y, z)) continue;
+      if (x == xo && y == yo && z == zo) continue;
+      xo = x, yo = y, zo = z;
+      if (!m->inb(x, y, z)) continue;
+      Cell &c = m->cells[(size_t)m->find_or_create(x, y, z)];
+      if (c.has_gaussian) {
+        double X[3];
+        double lik = cell_line_likelihood(c, po, pe, X);
+        const double dist = std::sqrt((origin[0] - X[0]) * (origin[0] - X[0]) + (origin[1] - X[1]) * (origin[1] - X[1]) +
+                                      (origin[2] - X[2]) * (origin[2] - X[2]));
+        if (dist > l) continue;  // the maximum-likelihood point lies beyond the measurement
+        const double l2 = std::sqrt((X[0] - pe[0]) * (X[0] - pe[0]) + (X[1] - pe[1]) * (X[1] - pe[1]) +
+                                    (X[2] - pe[2]) * (X[2] - pe[2]));
+        const double snoise = 0.5 * (dist / 30.0) + sensor_noise;
+        const double thr = std::exp(-0.5 * (l2 * l2) / (snoise * snoise));
+        lik *= (1.0 - thr);
+        if (lik < 0.3) continue;
+        lik = 0.1 * lik + 0.5;
+        const double logodd = std::log((1.0 - lik) / lik);
+        update_occupancy(c, (float)logodd, (float)occupancy_limit);
+        if (c.occ <= 0) c.has_gaussian = false;
+      } else {
+        update_occupancy(c, (float)-0.2, (float)occupancy_limit);
+        if (c.occ <= 0) c.has_gaussian = false;
+      }
+    }
+    if (m->add_point(p)) added++;
+  }
   return added;
 }
 

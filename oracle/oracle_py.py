@@ -84,6 +84,8 @@ def lib():
     L.orc_map_load_point_cloud.argtypes = [vp, vp, i64, C.c_double]
     L.orc_map_add_points.restype = i64
     L.orc_map_add_points.argtypes = [vp, vp, i64]
+    L.orc_map_add_point_cloud.restype = i64
+    L.orc_map_add_point_cloud.argtypes = [vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double]
     L.orc_map_compute_cells.argtypes = [vp, C.c_uint32, C.c_float]
     L.orc_map_from_cells.argtypes = [vp, C.POINTER(Grid), vp, i64, C.c_int]
     L.orc_map_grid.argtypes = [vp, C.POINTER(Grid)]
@@ -160,6 +162,13 @@ class OracleMap:
     def add_points(self, pts):
         pts = _pts4(pts)
         return lib().orc_map_add_points(self.h, pts.ctypes.data, pts.shape[0])
+
+    def add_point_cloud(self, origin, pts, classifier_th=0.06, maxz=100.0, sensor_noise=0.25, occupancy_limit=255.0):
+        """NDTMap::addPointCloud with the free-space ray trace (LazyGrid::traceLine) and occupancy update."""
+        pts = _pts4(pts)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        return lib().orc_map_add_point_cloud(self.h, o.ctypes.data, pts.ctypes.data, pts.shape[0], classifier_th, maxz,
+                                             sensor_noise, occupancy_limit)
 
     def compute_cells(self, maxnumpoints=int(1e9), occupancy_limit=255.0):
         lib().orc_map_compute_cells(self.h, maxnumpoints, occupancy_limit)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/ndtb.h but not exported by libndtb.so"
     assert set(api.abi_symbols()) == set(names)  # the Python mirror binds exactly the declared ABI
-    assert L.ndtb_version() == 101
+    assert L.ndtb_version() == 200
 
 
 def test_struct_layouts():

@@ -262,6 +262,7 @@ int ndtb_fuser_update(ndtb_fuser *f, const double *Tmotion16, const float *cloud
                       double *Tnow16, ndtb_result *res, double *cov36);
 ndtb_map *ndtb_fuser_map(ndtb_fuser *f); /* the node map (owned by the fuser) */
 int ndtb_fuser_pose(const ndtb_fuser *f, double *Tnow16);
+int ndtb_fuser_set_pose(ndtb_fuser *f, const double *Tnow16); /* NDTFeatureFuserHMT::Tnow is a public member (fuser_hmt.h:37) */
 
 /* ---- NDTFeatureGraph front end (ndt_feature/src/ndt_feature_src/ndt_feature_graph.cpp:24-144): a chain of nodes, each
  * a fuser with its own map in its own frame; a new node is spawned when the odometric path length inside the current

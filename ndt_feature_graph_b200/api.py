@@ -165,6 +165,7 @@ def load_library():
         "ndtb_fuser_update": (C.c_int, [vp, vp, vp, i64, C.c_int, C.c_int, vp, PR, vp]),
         "ndtb_fuser_map": (vp, [vp]),
         "ndtb_fuser_pose": (C.c_int, [vp, vp]),
+        "ndtb_fuser_set_pose": (C.c_int, [vp, vp]),
         "ndtb_graph_create": (C.c_int, [vp, C.POINTER(FuserParams), dbl, C.POINTER(vp)]),
         "ndtb_graph_destroy": (None, [vp]),
         "ndtb_graph_set_new_node_dist": (C.c_int, [vp, dbl]),

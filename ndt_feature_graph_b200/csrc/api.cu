@@ -21,6 +21,7 @@ namespace ndtb {
 // d2d.cu
 size_t match_smem_bytes(int table_entries);
 size_t opt_state_bytes();
+cudaError_t match_kernel_prepare(int smem_optin_bytes);
 cudaError_t launch_match(const MatchJob *d_jobs, const int *d_job_ids, int n_slots, int cluster, const MatchConfig &cfg,
                          ndtb_result *d_out, void *d_states, int resume, int pass_budget, int *d_unfinished, int *d_yielded,
                          cudaStream_t stream);
@@ -251,6 +252,7 @@ int define_grids(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::
     CU_TRY(ctx, cudaMemsetAsync(s->p + o_gs, 0, 64 * (size_t)W, st));
     ctx->launches += launch_guess((const BuildJob *)(s->p + o_j), (const int *)(s->p + o_w), W, max_pts, (const long long *)(s->p + o_ro),
                                   (double *)(s->p + o_rec), (double *)(s->p + o_gs), st);
+    CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaMemcpyAsync(gs.data(), s->p + o_gs, 64 * (size_t)W, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
     auto unkey = [](double bits) {
@@ -292,9 +294,33 @@ int define_grids(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::
 // load[i]: 1 = loadPointCloud semantics (grid (re)defined, map emptied), 2 = fresh map on the grid it already has,
 //          0 = addPointCloud (merge into the existing cells).
 using TraceSegs = std::vector<TraceSeg>;
+int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::vector<PointSrc> &pts,
+                      const std::vector<char> &load, const std::vector<double> &range, uint32_t maxnumpoints, float occ_limit,
+                      const std::vector<TraceSegs> *trace);
+
+// The build kernels put the map index on gridDim.y (limit 65535): larger batches are built slice by slice.
+constexpr int BUILD_SLICE = 32768;
 int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::vector<PointSrc> &pts,
                 const std::vector<char> &load, const std::vector<double> &range, uint32_t maxnumpoints, float occ_limit,
                 const std::vector<TraceSegs> *trace = nullptr) {
+  const size_t M = maps.size();
+  if (M <= (size_t)BUILD_SLICE) return build_batch_slice(ctx, maps, pts, load, range, maxnumpoints, occ_limit, trace);
+  for (size_t b = 0; b < M; b += BUILD_SLICE) {
+    const size_t e = std::min(M, b + BUILD_SLICE);
+    std::vector<ndtb_map *> m(maps.begin() + b, maps.begin() + e);
+    std::vector<PointSrc> p(pts.begin() + b, pts.begin() + e);
+    std::vector<char> l(load.begin() + b, load.begin() + e);
+    std::vector<double> r(range.begin() + b, range.begin() + e);
+    std::vector<TraceSegs> t;
+    if (trace) t.assign(trace->begin() + b, trace->begin() + e);
+    if (int rc = build_batch_slice(ctx, m, p, l, r, maxnumpoints, occ_limit, trace ? &t : nullptr)) return rc;
+  }
+  return NDTB_OK;
+}
+
+int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::vector<PointSrc> &pts,
+                      const std::vector<char> &load, const std::vector<double> &range, uint32_t maxnumpoints, float occ_limit,
+                      const std::vector<TraceSegs> *trace) {
   const int M = (int)maps.size();
   if (M == 0) return NDTB_OK;
   cudaStream_t st = ctx->stream;
@@ -409,6 +435,7 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
   if (L == 0) return NDTB_OK;
   CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
   ctx->launches += launch_mark(d_jobs, L, max_pts, any_trace, st);
+  CU_TRY(ctx, cudaGetLastError());
   std::vector<int> cnts_all(8 * (size_t)M), cnts(8 * (size_t)L);
   CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -482,10 +509,13 @@ int build_batch(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::v
     if (int rc = slab_alloc(ctx, sizeof(BuildJob) * L, s_vjobs)) return rc;
     CU_TRY(ctx, cudaMemcpyAsync(s_vjobs->p, vj.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
     ctx->launches += launch_trace_lists(d_jobs, (const BuildJob *)s_vjobs->p, L, max_pts, max_vis, max_ntb, max_cells, st);
+    CU_TRY(ctx, cudaGetLastError());
   }
   ctx->launches += launch_cells(d_jobs, L, max_pts, max_ntb, max_cells, st);
+  CU_TRY(ctx, cudaGetLastError());
   pt.mark("cells");
   ctx->launches += launch_gview(d_jobs, L, max_ntb, st);
+  CU_TRY(ctx, cudaGetLastError());
   CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
   for (int l = 0; l < L; l++) std::memcpy(&cnts[8 * l], &cnts_all[8 * (size_t)live_idx[l]], 32);
@@ -724,6 +754,12 @@ int ndtb_ctx_create(int device, void *stream, ndtb_ctx **out) {
   }
   uint64_t thr = UINT64_MAX;
   cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  if (match_kernel_prepare(c->smem_optin) != cudaSuccess) {
+    cudaMemPoolDestroy(c->pool);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return NDTB_ERR_CUDA;
+  }
   *out = c;
   return NDTB_OK;
 }

@@ -526,13 +526,18 @@ size_t match_smem_bytes(int table_entries) {
 }
 size_t opt_state_bytes() { return sizeof(OptState); }
 
+// The dynamic shared memory limit is an attribute of the FUNCTION on a device, shared by every context / host thread that
+// launches it: it is raised once per context creation to the device's opt-in maximum and never lowered per launch (two
+// threads with different table sizes would otherwise race on it).
+cudaError_t match_kernel_prepare(int smem_optin_bytes) {
+  return cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_bytes);
+}
+
 // n_slots registrations (job_ids[slot] or slot itself), each on a cluster of `cluster` CTAs
 cudaError_t launch_match(const MatchJob *d_jobs, const int *d_job_ids, int n_slots, int cluster, const MatchConfig &cfg,
                          ndtb_result *d_out, void *d_states, int resume, int pass_budget, int *d_unfinished, int *d_yielded,
                          cudaStream_t stream) {
   const size_t smem = match_smem_bytes(cfg.table_smem_entries);
-  cudaError_t e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(n_slots * cluster));
   lc.blockDim = dim3(MATCH_THREADS);
@@ -614,20 +619,20 @@ __device__ __forceinline__ void outer_upper(const double *g, double *o) {
     for (int b = a; b < 6; b++) o[n++] += g[a] * g[b];
 }
 
-// grid (chunks, jobs): thread per source cell, hits processed serially; per-target sums by fp64 atomics.
+// grid (jobs, chunks): thread per source cell, hits processed serially; per-target sums by fp64 atomics.
 __global__ void __launch_bounds__(COV_THREADS)
 cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_result *__restrict__ res,
                 const long long *__restrict__ gt_off, double *__restrict__ gt, double *__restrict__ partial,
                 const int *__restrict__ yielded, int mode /*0 all, 1 not yielded, 2 yielded only*/) {
-  if (mode && (yielded[blockIdx.y] != 0) != (mode == 2)) return;
-  const MatchJob &job = jobs[blockIdx.y];
+  if (mode && (yielded[blockIdx.x] != 0) != (mode == 2)) return;
+  const MatchJob &job = jobs[blockIdx.x];
   __shared__ double P[12];
   __shared__ GridDesc grid;
   __shared__ double red[(COV_THREADS / 32) * COV_W];
-  const bool skip = res && !res[blockIdx.y].pose_changed;
+  const bool skip = res && !res[blockIdx.x].pose_changed;
   if (threadIdx.x == 0) {
     grid = job.tgt.g;
-    const Pose T = pose_from_cm(res ? res[blockIdx.y].T : job.T0);
+    const Pose T = pose_from_cm(res ? res[blockIdx.x].T : job.T0);
     for (int i = 0; i < 9; i++) P[i] = T.R[i];
     for (int i = 0; i < 3; i++) P[9 + i] = T.t[i];
   }
@@ -636,9 +641,9 @@ cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_r
 #pragma unroll
   for (int j = 0; j < COV_W; j++) acc[j] = 0.0;
   const int k = cfg.n_neighbours;
-  double *gtj = gt + gt_off[blockIdx.y] * 6;
+  double *gtj = gt + gt_off[blockIdx.x] * 6;
   if (!skip) {
-    for (int i = blockIdx.x * COV_THREADS + threadIdx.x; i < job.src_ng; i += gridDim.x * COV_THREADS) {
+    for (int i = blockIdx.y * COV_THREADS + threadIdx.x; i < job.src_ng; i += gridDim.y * COV_THREADS) {
       double mu[3], C[6], gs[6] = {0, 0, 0, 0, 0, 0};
       move_cell(P, job.src_gcell + (size_t)i * GC, mu, C);
       int ix, iy, iz;
@@ -692,7 +697,7 @@ cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_r
   if (threadIdx.x < COV_W) {
     double s = 0.0;
     for (int w = 0; w < COV_THREADS / 32; w++) s += red[w * COV_W + threadIdx.x];
-    partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * COV_W + threadIdx.x] = s;
+    partial[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * COV_W + threadIdx.x] = s;
   }
 }
 
@@ -766,7 +771,7 @@ cov_finalize_kernel(const MatchJob *__restrict__ jobs, const ndtb_result *__rest
 cudaError_t launch_covariance(const MatchJob *d_jobs, int n_jobs, const MatchConfig &cfg, const ndtb_result *d_res,
                               const long long *d_gt_off, double *d_gt, double *d_partial, int n_chunks,
                               double *d_cov36, int *d_status, const int *d_yielded, int mode, cudaStream_t stream) {
-  dim3 grid(n_chunks, n_jobs);
+  dim3 grid(n_jobs, n_chunks);  // jobs on x: no 65535 limit on the batch size
   cov_pass_kernel<<<grid, COV_THREADS, 0, stream>>>(d_jobs, cfg, d_res, d_gt_off, d_gt, d_partial, d_yielded, mode);
   cov_finalize_kernel<<<n_jobs, COV_THREADS, 0, stream>>>(d_jobs, d_res, d_gt_off, d_gt, d_partial, n_chunks, d_cov36,
                                                          d_status, d_yielded, mode);

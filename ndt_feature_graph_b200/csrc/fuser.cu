@@ -153,6 +153,12 @@ int ndtb_fuser_pose(const ndtb_fuser *f, double *Tnow16) {
   return NDTB_OK;
 }
 
+int ndtb_fuser_set_pose(ndtb_fuser *f, const double *Tnow16) {
+  if (!f || !Tnow16) return NDTB_ERR_ARG;
+  f->Tnow = ndtb::pose_from_cm(Tnow16);
+  return NDTB_OK;
+}
+
 int ndtb_fuser_initialize(ndtb_fuser *f, const double *init_pose16, const float *cloud, int64_t n, int mem) {
   if (!f || !init_pose16 || n < 0 || (n > 0 && !cloud)) return NDTB_ERR_ARG;
   const float *d_raw;

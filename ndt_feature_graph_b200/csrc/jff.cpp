@@ -102,9 +102,26 @@ int ndtb_jff_read_cells(const char *path, ndtb_grid *g, ndtb_cell *cells, int64_
       std::fclose(f);
       return NDTB_ERR_GRID;
     }
-    g->size[a] = (int32_t)std::fabs(std::ceil(size_m / g->cell[a]));  // LazyGrid::setSize
+    const double cells_axis = std::fabs(std::ceil(size_m / g->cell[a]));  // LazyGrid::setSize
+    if (!(cells_axis >= 1.0 && cells_axis <= 1048576.0) || !std::isfinite(g->center[a])) {  // also rejects NaN / inf headers
+      std::fclose(f);
+      return NDTB_ERR_GRID;
+    }
+    g->size[a] = (int32_t)cells_axis;
   }
-  const int64_t total = (int64_t)g->size[0] * g->size[1] * g->size[2];
+  const int64_t total = (int64_t)g->size[0] * g->size[1] * g->size[2];  // <= 2^60: no overflow
+  {  // a truncated file is refused before anything is read
+    const long here = std::ftell(f);
+    if (here < 0 || std::fseek(f, 0, SEEK_END) != 0) {
+      std::fclose(f);
+      return NDTB_ERR_ARG;
+    }
+    const long end = std::ftell(f);
+    if (total > ((int64_t)1 << 31) || (int64_t)(end - here) < total * (int64_t)REC || std::fseek(f, here, SEEK_SET) != 0) {
+      std::fclose(f);
+      return NDTB_ERR_GRID;
+    }
+  }
   std::vector<unsigned char> buf(REC * 4096);
   int64_t found = 0, done = 0;
   bool ok = total > 0;

@@ -75,6 +75,11 @@ class NDTFeatureFuserHMT:
         self.e.check(self.e.L.ndtb_fuser_pose(self.h, out.ctypes.data))
         return _pose(out)
 
+    @Tnow.setter
+    def Tnow(self, T):
+        Tc = _cm(T)
+        self.e.check(self.e.L.ndtb_fuser_set_pose(self.h, Tc.ctypes.data))
+
 
 class _NodeView:
     """One node of the graph: .T, .Tlocal_odom, .Tlocal_fuse, .nbUpdates, .map.map (the node's NDT map)."""

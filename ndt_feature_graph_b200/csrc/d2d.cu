@@ -24,13 +24,19 @@ namespace cg = cooperative_groups;
 namespace ndtb {
 
 #ifndef NDTB_MATCH_THREADS
-#define NDTB_MATCH_THREADS 256
+#define NDTB_MATCH_THREADS 384  // 12 warps at 168 registers (B200 A/B, 592 C2 pairs: 256 thr 62.1 ms, 384 thr 56.8 ms, 512 thr + Hessian sums in shared memory 57.1 ms)
 #endif
 #ifndef NDTB_GRAD2
 #define NDTB_GRAD2 0  // gradient pass: two pairs per lane interleaved (measured slower on B200: spills)
 #endif
 #ifndef NDTB_PUSH_SCAN
-#define NDTB_PUSH_SCAN 1  // 1: one warp prefix scan per probe column; 0: one ballot per pushed hit
+#define NDTB_PUSH_SCAN 0  // 1: one warp prefix scan per probe column; 0: one ballot per pushed hit (faster from 384 threads up)
+#endif
+#ifndef NDTB_HESS_SMEM
+#define NDTB_HESS_SMEM 0  // 1: Hessian sums in per-lane shared-memory slots (needed at 512 threads / 128 registers); 0: in registers
+#endif
+#ifndef NDTB_MATCH_MINBLOCKS
+#define NDTB_MATCH_MINBLOCKS 1
 #endif
 constexpr int MATCH_THREADS = NDTB_MATCH_THREADS;
 constexpr int MATCH_WARPS = MATCH_THREADS / 32;
@@ -43,6 +49,13 @@ constexpr unsigned FULL = 0xffffffffu;
 struct WarpScratch {
   double stage[GC][32];  // moved source cells of the current round, SoA: stage[k][lane]
   unsigned queue[QCAP];  // (source lane << 27) | target slot
+};
+
+// Hessian sums of the registration kernel: one shared-memory slot per lane and entry, hs[i * MATCH_THREADS + tid] (conflict
+// free), so that the 21 running sums do not compete with the pair arithmetic for registers.
+struct SmemAcc {
+  double *slot;  // &hs[tid]
+  __device__ __forceinline__ void add(int i, double v) const { slot[i * MATCH_THREADS] += v; }
 };
 
 struct PassCtx {
@@ -90,8 +103,8 @@ __device__ __forceinline__ unsigned long long expand_y(unsigned a) {
 }
 __device__ __forceinline__ unsigned long long expand_z(unsigned a) { return (unsigned long long)a * 0x1111111111111111ull; }
 
-template <bool HESS>
-__device__ __forceinline__ void process_entry(const PassCtx &c, const WarpScratch &ws, unsigned e, double *acc) {
+template <bool HESS, class HA>
+__device__ __forceinline__ void process_entry(const PassCtx &c, const WarpScratch &ws, unsigned e, double *acc, const HA &ha) {
   const int sl = e >> 27;
   const int slot = e & 0x7FFFFFF;
   double C[6], m[3], S[6];
@@ -103,7 +116,7 @@ __device__ __forceinline__ void process_entry(const PassCtx &c, const WarpScratc
   for (int j = 0; j < 3; j++) m[j] = __ldg(t + j);
 #pragma unroll
   for (int j = 0; j < 6; j++) S[j] = __ldg(t + 3 + j);
-  if (pair_contrib<HESS>(mu0, mu1, mu2, C, m, S, c.lfd1, c.lfd2, acc, nullptr)) acc[ACC_PAIRS] += 1.0;
+  if (pair_contrib_acc<HESS, HA>(mu0, mu1, mu2, C, m, S, c.lfd1, c.lfd2, acc, ha, nullptr)) acc[ACC_PAIRS] += 1.0;
 }
 
 // gradient pass: two pairs per lane at once (independent dependency chains interleave, hiding the fp64 / exp / load
@@ -123,8 +136,9 @@ __device__ __forceinline__ void process_entry2(const PassCtx &c, const WarpScrat
   pair_grad_nb(ws.stage[0][sl1], ws.stage[1][sl1], ws.stage[2][sl1], C1, m1, S1, c.lfd1, c.lfd2, live1, acc, acc + ACC_PAIRS);
 }
 
-template <bool HESS>
-__device__ __forceinline__ void drain_batches(const PassCtx &c, WarpScratch &ws, int &qcount, int keep, int lane, double *acc) {
+template <bool HESS, class HA>
+__device__ __forceinline__ void drain_batches(const PassCtx &c, WarpScratch &ws, int &qcount, int keep, int lane, double *acc,
+                                              const HA &ha) {
   // process full batches of 32 pairs from the top of the queue until fewer than `keep` + 32 entries are left
   if (!HESS && NDTB_GRAD2) {
     while (qcount >= keep + 64) {
@@ -134,7 +148,7 @@ __device__ __forceinline__ void drain_batches(const PassCtx &c, WarpScratch &ws,
   }
   while (qcount >= keep + 32) {
     qcount -= 32;
-    process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
+    process_entry<HESS, HA>(c, ws, ws.queue[qcount + lane], acc, ha);
   }
 }
 
@@ -164,8 +178,8 @@ __device__ __forceinline__ void move_cell(const double *P, const double *s, doub
 }
 
 // One derivative pass over the source cells assigned to this warp (rounds wg, wg+nwg, ...).
-template <bool HESS>
-__device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int wg, int nwg, double *acc) {
+template <bool HESS, class HA>
+__device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int wg, int nwg, double *acc, const HA &ha) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int k = c.k;
@@ -223,7 +237,7 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
         if (total == 0) continue;
         if (qcount + total > QCAP) {  // make room: drain the full batches
           __syncwarp();
-          drain_batches<HESS>(c, ws, qcount, 0, lane, acc);
+          drain_batches<HESS, HA>(c, ws, qcount, 0, lane, acc, ha);
           __syncwarp();
         }
         if (qcount + total <= QCAP) {
@@ -250,7 +264,7 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
                 __syncwarp();
                 while (qcount >= 32) {
                   qcount -= 32;
-                  process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
+                  process_entry<HESS, HA>(c, ws, ws.queue[qcount + lane], acc, ha);
                 }
                 __syncwarp();
               }
@@ -281,7 +295,7 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
               __syncwarp();
               while (qcount >= 32) {
                 qcount -= 32;
-                process_entry<HESS>(c, ws, ws.queue[qcount + lane], acc);
+                process_entry<HESS, HA>(c, ws, ws.queue[qcount + lane], acc, ha);
               }
               __syncwarp();
             }
@@ -299,9 +313,9 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
     }
     // end of round: the staged cells are about to be overwritten — drain everything
     __syncwarp();
-    drain_batches<HESS>(c, ws, qcount, 0, lane, acc);
+    drain_batches<HESS, HA>(c, ws, qcount, 0, lane, acc, ha);
     if (qcount > 0) {
-      if (lane < qcount) process_entry<HESS>(c, ws, ws.queue[lane], acc);
+      if (lane < qcount) process_entry<HESS, HA>(c, ws, ws.queue[lane], acc, ha);
       qcount = 0;
     }
     __syncwarp();
@@ -309,12 +323,14 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
 }
 
 // deterministic block reduction of n per-thread accumulators -> sums[n] (shared)
-__device__ __forceinline__ void block_reduce(const double *acc, int n, double *red, double *sums, int nwarps) {
+// hs != nullptr: the Hessian entries (j >= ACC_H) are read from the per-lane shared-memory slots hs[(j - ACC_H) * stride + tid]
+__device__ __forceinline__ void block_reduce(const double *acc, int n, double *red, double *sums, int nwarps,
+                                             const double *hs = nullptr, int stride = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < ACC_TOTAL; j++) {
     if (j < n || j == ACC_PAIRS) {
-      double v = acc[j];
+      double v = (hs && j >= ACC_H && j < ACC_PAIRS) ? hs[(j - ACC_H) * stride + threadIdx.x] : acc[j];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
       if (lane == 0) red[warp * ACC_TOTAL + j] = v;
@@ -398,7 +414,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // broadcasts the next pose the same way.  job_ids (optional) selects the jobs of this launch; states/pass_budget
 // implement the straggler hand-over: a registration that has used pass_budget derivative passes saves its optimiser
 // state and is finished by a second launch with a wider cluster.
-__global__ void __launch_bounds__(MATCH_THREADS, 1)
+__global__ void __launch_bounds__(MATCH_THREADS, NDTB_MATCH_MINBLOCKS)
 match_kernel(const MatchJob *__restrict__ jobs, const int *__restrict__ job_ids, MatchConfig cfg, ndtb_result *__restrict__ out,
              OptState *__restrict__ states, int resume, int pass_budget, int *__restrict__ unfinished /*[0]=count, ids follow*/,
              int *__restrict__ yielded /*[n jobs] set to 1 for a registration handed to the finishing launch*/) {
@@ -409,6 +425,8 @@ match_kernel(const MatchJob *__restrict__ jobs, const int *__restrict__ job_ids,
   HashEntry *stab = reinterpret_cast<HashEntry *>(dyn_smem);
   MatchShared &sh = *reinterpret_cast<MatchShared *>(dyn_smem + (size_t)cfg.table_smem_entries * sizeof(HashEntry));
   WarpScratch *wsp = reinterpret_cast<WarpScratch *>(reinterpret_cast<unsigned char *>(&sh) + ((sizeof(MatchShared) + 15) & ~(size_t)15));
+  double *hs = reinterpret_cast<double *>(wsp + MATCH_WARPS);  // [21][MATCH_THREADS] Hessian sums, one slot per lane
+  const SmemAcc hacc{hs + threadIdx.x};
   const int slot = blockIdx.x / G;
   const int jid = job_ids ? job_ids[slot] : slot;
   const MatchJob &job = jobs[jid];
@@ -461,11 +479,20 @@ match_kernel(const MatchJob *__restrict__ jobs, const int *__restrict__ job_ids,
     double acc[ACC_TOTAL];
 #pragma unroll
     for (int j = 0; j < ACC_TOTAL; j++) acc[j] = 0.0;
-    if (hess)
-      d2d_pass<true>(c, sh.ctl.P, wsp[warp], rank * MATCH_WARPS + warp, G * MATCH_WARPS, acc);
-    else
-      d2d_pass<false>(c, sh.ctl.P, wsp[warp], rank * MATCH_WARPS + warp, G * MATCH_WARPS, acc);
-    block_reduce(acc, hess ? 28 : 7, sh.red, sh.sums, MATCH_WARPS);
+    if (hess) {
+#if NDTB_HESS_SMEM
+#pragma unroll
+      for (int j = 0; j < 21; j++) hs[j * MATCH_THREADS + threadIdx.x] = 0.0;
+      d2d_pass<true, SmemAcc>(c, sh.ctl.P, wsp[warp], rank * MATCH_WARPS + warp, G * MATCH_WARPS, acc, hacc);
+      block_reduce(acc, 28, sh.red, sh.sums, MATCH_WARPS, hs, MATCH_THREADS);
+#else
+      d2d_pass<true, RegAcc>(c, sh.ctl.P, wsp[warp], rank * MATCH_WARPS + warp, G * MATCH_WARPS, acc, RegAcc{acc});
+      block_reduce(acc, 28, sh.red, sh.sums, MATCH_WARPS);
+#endif
+    } else {
+      d2d_pass<false, SmemAcc>(c, sh.ctl.P, wsp[warp], rank * MATCH_WARPS + warp, G * MATCH_WARPS, acc, hacc);
+      block_reduce(acc, 7, sh.red, sh.sums, MATCH_WARPS);
+    }
     passes++;
     if (G > 1) {
       if (threadIdx.x < ACC_TOTAL) cluster.map_shared_rank(&sh.csums[0][0], 0)[rank * ACC_TOTAL + threadIdx.x] = sh.sums[threadIdx.x];
@@ -522,7 +549,7 @@ match_kernel(const MatchJob *__restrict__ jobs, const int *__restrict__ job_ids,
 
 size_t match_smem_bytes(int table_entries) {
   return (size_t)table_entries * sizeof(HashEntry) + ((sizeof(MatchShared) + 15) & ~(size_t)15) +
-         MATCH_WARPS * sizeof(WarpScratch);
+         MATCH_WARPS * sizeof(WarpScratch) + (NDTB_HESS_SMEM ? (size_t)21 * MATCH_THREADS * sizeof(double) : 0);
 }
 size_t opt_state_bytes() { return sizeof(OptState); }
 
@@ -582,7 +609,7 @@ deriv_kernel(const MatchJob *__restrict__ job_p, MatchConfig cfg, double *__rest
 #pragma unroll
   for (int j = 0; j < ACC_TOTAL; j++) acc[j] = 0.0;
   const int warp = threadIdx.x >> 5;
-  d2d_pass<HESS>(c, sh.P, ws[warp], blockIdx.x * DERIV_WARPS + warp, gridDim.x * DERIV_WARPS, acc);
+  d2d_pass<HESS, RegAcc>(c, sh.P, ws[warp], blockIdx.x * DERIV_WARPS + warp, gridDim.x * DERIV_WARPS, acc, RegAcc{acc});
   block_reduce(acc, HESS ? 28 : 7, sh.red, sh.sums, DERIV_WARPS);
   if (threadIdx.x < ACC_TOTAL) partial[blockIdx.x * ACC_TOTAL + threadIdx.x] = sh.sums[threadIdx.x];
 }

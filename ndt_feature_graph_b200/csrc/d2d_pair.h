@@ -39,10 +39,17 @@ NDTB_HD constexpr int hidx(int p, int q) { return ACC_H + p * 6 - (p * (p - 1)) 
 // Adds the pair's contribution to acc.  g6 (optional, may be nullptr) receives this pair's own gradient
 // contribution (used by covariance()).  Returns false if the pair is skipped (C+S not invertible by
 // Eigen's computeInverseAndDetWithCheck threshold, or non-finite Mahalanobis distance).
-template <bool HESS>
-NDTB_HD bool pair_contrib(const double mu0, const double mu1, const double mu2, const double *C /*6*/,
-                          const double *m /*3*/, const double *S /*6*/, double lfd1, double lfd2, double *acc,
-                          double *g6) {
+// Where the 21 Hessian sums of a thread live: RegAcc = in the thread's accumulator array (acc[ACC_H + i]); a kernel
+// that wants the registers for the pair arithmetic passes its own policy (d2d.cu: one shared-memory slot per lane).
+struct RegAcc {
+  double *acc;
+  NDTB_HD void add(int i, double v) const { acc[ACC_H + i] += v; }
+};
+
+template <bool HESS, class HA>
+NDTB_HD bool pair_contrib_acc(const double mu0, const double mu1, const double mu2, const double *C /*6*/,
+                              const double *m /*3*/, const double *S /*6*/, double lfd1, double lfd2, double *acc,
+                              const HA &hacc, double *g6) {
   const double x0 = mu0 - m[0], x1 = mu1 - m[1], x2 = mu2 - m[2];
   const double a00 = C[0] + S[0], a01 = C[1] + S[1], a02 = C[2] + S[2];
   const double a11 = C[3] + S[3], a12 = C[4] + S[4], a22 = C[5] + S[5];
@@ -51,7 +58,11 @@ NDTB_HD bool pair_contrib(const double mu0, const double mu1, const double mu2, 
   const double c20 = a01 * a12 - a02 * a11;
   const double det = c00 * a00 + c10 * a01 + c20 * a02;
   if (!(fabs(det) > 1e-12)) return false;
+#ifdef __CUDA_ARCH__
+  const double id = __drcp_rn(det);  // the correctly rounded reciprocal == 1.0 / det bit for bit, a third of the instructions
+#else
   const double id = 1.0 / det;
+#endif
   const double b00 = c00 * id, b01 = c10 * id, b02 = c20 * id;
   const double b11 = (a00 * a22 - a02 * a02) * id;
   const double b12 = (a02 * a01 - a00 * a12) * id;
@@ -102,24 +113,23 @@ NDTB_HD bool pair_contrib(const double mu0, const double mu1, const double mu2, 
                Dz2 = b02 * dz0 + b12 * dz1 + b22 * dz2;
   const double qv = q0 * v0 + q1 * v1 + q2 * v2;
   const double hl = lfd2 * 0.5;
-  double *H = acc;
   // translation-translation
-  H[hidx(0, 0)] += factor * (2.0 * b00 - hl * Q[0] * Q[0]);
-  H[hidx(0, 1)] += factor * (2.0 * b01 - hl * Q[0] * Q[1]);
-  H[hidx(0, 2)] += factor * (2.0 * b02 - hl * Q[0] * Q[2]);
-  H[hidx(1, 1)] += factor * (2.0 * b11 - hl * Q[1] * Q[1]);
-  H[hidx(1, 2)] += factor * (2.0 * b12 - hl * Q[1] * Q[2]);
-  H[hidx(2, 2)] += factor * (2.0 * b22 - hl * Q[2] * Q[2]);
+  hacc.add(hidx(0, 0) - ACC_H, factor * (2.0 * b00 - hl * Q[0] * Q[0]));
+  hacc.add(hidx(0, 1) - ACC_H, factor * (2.0 * b01 - hl * Q[0] * Q[1]));
+  hacc.add(hidx(0, 2) - ACC_H, factor * (2.0 * b02 - hl * Q[0] * Q[2]));
+  hacc.add(hidx(1, 1) - ACC_H, factor * (2.0 * b11 - hl * Q[1] * Q[1]));
+  hacc.add(hidx(1, 2) - ACC_H, factor * (2.0 * b12 - hl * Q[1] * Q[2]));
+  hacc.add(hidx(2, 2) - ACC_H, factor * (2.0 * b22 - hl * Q[2] * Q[2]));
   // translation-rotation
-  H[hidx(0, 3)] += factor * (2.0 * Dx0 - hl * Q[0] * Q[3]);
-  H[hidx(1, 3)] += factor * (2.0 * Dx1 - hl * Q[1] * Q[3]);
-  H[hidx(2, 3)] += factor * (2.0 * Dx2 - hl * Q[2] * Q[3]);
-  H[hidx(0, 4)] += factor * (2.0 * Dy0 - hl * Q[0] * Q[4]);
-  H[hidx(1, 4)] += factor * (2.0 * Dy1 - hl * Q[1] * Q[4]);
-  H[hidx(2, 4)] += factor * (2.0 * Dy2 - hl * Q[2] * Q[4]);
-  H[hidx(0, 5)] += factor * (2.0 * Dz0 - hl * Q[0] * Q[5]);
-  H[hidx(1, 5)] += factor * (2.0 * Dz1 - hl * Q[1] * Q[5]);
-  H[hidx(2, 5)] += factor * (2.0 * Dz2 - hl * Q[2] * Q[5]);
+  hacc.add(hidx(0, 3) - ACC_H, factor * (2.0 * Dx0 - hl * Q[0] * Q[3]));
+  hacc.add(hidx(1, 3) - ACC_H, factor * (2.0 * Dx1 - hl * Q[1] * Q[3]));
+  hacc.add(hidx(2, 3) - ACC_H, factor * (2.0 * Dx2 - hl * Q[2] * Q[3]));
+  hacc.add(hidx(0, 4) - ACC_H, factor * (2.0 * Dy0 - hl * Q[0] * Q[4]));
+  hacc.add(hidx(1, 4) - ACC_H, factor * (2.0 * Dy1 - hl * Q[1] * Q[4]));
+  hacc.add(hidx(2, 4) - ACC_H, factor * (2.0 * Dy2 - hl * Q[2] * Q[4]));
+  hacc.add(hidx(0, 5) - ACC_H, factor * (2.0 * Dz0 - hl * Q[0] * Q[5]));
+  hacc.add(hidx(1, 5) - ACC_H, factor * (2.0 * Dz1 - hl * Q[1] * Q[5]));
+  hacc.add(hidx(2, 5) - ACC_H, factor * (2.0 * Dz2 - hl * Q[2] * Q[5]));
   // rotation-rotation (a<=b): 2 d_a.D_b + 2 v_a q_b - 2 delta q.v - 2 n_a.cn_b
   // n_x.cn_b = q2*cn_b1 - q1*cn_b2 ; n_y.cn_b = -q2*cn_b0 + q0*cn_b2 ; n_z.cn_b = q1*cn_b0 - q0*cn_b1
   const double xx = dx0 * Dx0 + dx1 * Dx1 + dx2 * Dx2 + v0 * q0 - qv - (q2 * cnx1 - q1 * cnx2);
@@ -128,13 +138,19 @@ NDTB_HD bool pair_contrib(const double mu0, const double mu1, const double mu2, 
   const double yy = dy0 * Dy0 + dy1 * Dy1 + dy2 * Dy2 + v1 * q1 - qv - (q0 * cny2 - q2 * cny0);
   const double yz = dy0 * Dz0 + dy1 * Dz1 + dy2 * Dz2 + v1 * q2 - (q0 * cnz2 - q2 * cnz0);
   const double zz = dz0 * Dz0 + dz1 * Dz1 + dz2 * Dz2 + v2 * q2 - qv - (q1 * cnz0 - q0 * cnz1);
-  H[hidx(3, 3)] += factor * (2.0 * xx - hl * Q[3] * Q[3]);
-  H[hidx(3, 4)] += factor * (2.0 * xy - hl * Q[3] * Q[4]);
-  H[hidx(3, 5)] += factor * (2.0 * xz - hl * Q[3] * Q[5]);
-  H[hidx(4, 4)] += factor * (2.0 * yy - hl * Q[4] * Q[4]);
-  H[hidx(4, 5)] += factor * (2.0 * yz - hl * Q[4] * Q[5]);
-  H[hidx(5, 5)] += factor * (2.0 * zz - hl * Q[5] * Q[5]);
+  hacc.add(hidx(3, 3) - ACC_H, factor * (2.0 * xx - hl * Q[3] * Q[3]));
+  hacc.add(hidx(3, 4) - ACC_H, factor * (2.0 * xy - hl * Q[3] * Q[4]));
+  hacc.add(hidx(3, 5) - ACC_H, factor * (2.0 * xz - hl * Q[3] * Q[5]));
+  hacc.add(hidx(4, 4) - ACC_H, factor * (2.0 * yy - hl * Q[4] * Q[4]));
+  hacc.add(hidx(4, 5) - ACC_H, factor * (2.0 * yz - hl * Q[4] * Q[5]));
+  hacc.add(hidx(5, 5) - ACC_H, factor * (2.0 * zz - hl * Q[5] * Q[5]));
   return true;
+}
+
+template <bool HESS>
+NDTB_HD bool pair_contrib(const double mu0, const double mu1, const double mu2, const double *C /*6*/, const double *m /*3*/,
+                          const double *S /*6*/, double lfd1, double lfd2, double *acc, double *g6) {
+  return pair_contrib_acc<HESS, RegAcc>(mu0, mu1, mu2, C, m, S, lfd1, lfd2, acc, RegAcc{acc}, g6);
 }
 
 // Branch-free gradient-only variant: a skipped pair contributes exact zeros through selects, so two calls on

@@ -152,6 +152,12 @@ int ndtb_map_initialize(ndtb_map *m, double cx, double cy, double cz, double sx,
  * (pcl::PointXYZ: x,y,z,pad), in host or device memory.  *n_binned (optional) = points kept. */
 int ndtb_map_load_point_cloud(ndtb_map *m, const float *pts, int64_t n, double range_limit, int mem,
                               int64_t *n_binned);
+/* NDTMap::loadPointCloudCentroid(pc, origin, old_centroid, map_size, range_limit) [upstream] — the loadCentroid branch
+ * of the local-map build, ndt_feature_fuser_hmt.cpp:199-217: the grid centre is old_centroid moved by a whole number of
+ * cells towards origin (floor((origin - old_centroid) / cell) * cell per axis), its size is map_size, and points farther
+ * than range_limit from ORIGIN are dropped. */
+int ndtb_map_load_point_cloud_centroid(ndtb_map *m, const float *pts, int64_t n, int mem, const double *origin3,
+                                       const double *old_centroid3, const double *map_size3, double range_limit);
 /* NDTMap::addPointCloud, end-point binning only (no ray tracing; see ndtb_map_add_point_cloud) */
 int ndtb_map_add_points(ndtb_map *m, const float *pts, int64_t n, int mem, int64_t *n_binned);
 /* NDTMap::addPointCloud(origin, pc, classifierTh, maxz, sensor_noise, occupancy_limit) [upstream] WITH the free-space ray
@@ -185,6 +191,19 @@ int64_t ndtb_map_point_indices(const ndtb_map *m, const float *pts, int64_t n, i
  * out43 = score, g[6], H[36] row-major (H zero when !want_hessian); n_pairs optional. */
 int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T,
                          const ndtb_params *p, int want_hessian, double *out43, int64_t *n_pairs);
+/* The cell-vector overload the reference's optimiser calls (ndt_matcher_d2d_fusion.h:856,617,444):
+ * derivativesNDT(const std::vector<NDTCell*> &sourceNDT, const NDTMap &targetNDT, g, H, computeHessian) on host copies of
+ * cells that were already moved (pseudoTransformNDT, :840); T (optional, NULL = identity) moves them further. */
+int ndtb_d2d_derivatives_cells(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_cell *src, int64_t n, const double *T,
+                               const ndtb_params *p, int want_hessian, double *out43, int64_t *n_pairs);
+/* NDTMatcherD2D::lineSearchMT(increment, sourceNDT, targetNDT) [upstream] (ndt_matcher_d2d_fusion.h:1013; the in-repo twin
+ * is lineSearchMTFusion :390-793): More-Thuente step length along `increment6` for the cells as they are; increment6 may be
+ * negated in place (wrong-direction case, :462).  Every trial evaluation is one gradient pass on the device. */
+int ndtb_d2d_line_search_cells(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_cell *src, int64_t n, double *increment6,
+                               const ndtb_params *p, double *step);
+/* NDTMatcherD2D::MoreThuente::cstep [upstream] == MINPACK dcstep (ndt_matcher_d2d_fusion.h:347,366,756,775): returns info */
+int ndtb_mt_cstep(double *stx, double *fx, double *dx, double *sty, double *fy, double *dy, double *stp, double fp, double dp,
+                  int *brackt, double stmin, double stmax);
 int ndtb_d2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0,
                    const ndtb_params *p, ndtb_result *res);
 /* matchFusion with useNDT=true, useFeat=false: soft constraint Q = Tcov^-1 (Tcov36 row-major 6x6) */
@@ -278,9 +297,46 @@ int64_t ndtb_graph_num_nodes(const ndtb_graph *g);
 int ndtb_graph_node(ndtb_graph *g, int64_t k, double *T16, double *Tlocal_odom16, double *Tlocal_fuse16, ndtb_map **map,
                     int32_t *nb_updates);
 
+/* ---- result hand-off formats (host code, no GPU; csrc/formats.cpp) ---------------------------------------------------
+ * ndt_feature/NDTEdgeMsg: the ROS1 wire bytes of one refined link, as edgeToMsg builds it
+ * (ndt_feature/include/ndt_feature/ndtgraph_conversion.h:17-34; ndt_feature/msg/NDTEdgeMsg.msg): u32 ref_idx, u32 mov_idx,
+ * geometry_msgs/Pose T, Float64MultiArray cov (3x3), Float64MultiArray cov_3d (6x6, or empty when cov36 == NULL), f64 score.
+ * cov9 / cov36 row-major.  Returns the message length (write happens only when cap suffices) or < 0. */
+int64_t ndtb_edge_msg_pack(uint32_t ref_idx, uint32_t mov_idx, const double *T16, const double *cov9, const double *cov36,
+                           double score, uint8_t *out, int64_t cap);
+/* msgToEdge (ndtgraph_conversion.h:104-145) */
+int ndtb_edge_msg_unpack(const uint8_t *buf, int64_t len, uint32_t *ref_idx, uint32_t *mov_idx, double *T16, double *cov9,
+                         double *cov36, int32_t *has_cov36, double *score);
+/* saveAffine3d / loadAffine3d of NDTFeatureNode::save / load (ndt_feature_node.h:100-152): the boost text archives
+ * mapping{k}.T, ...local_odom.T, ...local_fuse.T the reference ships (byte-compatible) */
+int ndtb_pose_archive_write(const char *path, const double *T16);
+int ndtb_pose_archive_read(const char *path, double *T16);
+/* transformToEvalString (planar = 0) / transformToEval2dString (planar = 1), utils.h:243-259: one line of the est / gt
+ * trajectory files ("x y z qx qy qz qw\n", 15 significant digits).  Returns the length or < 0. */
+int ndtb_eval_string(const double *T16, int planar, char *out, int32_t cap);
+
+/* ---- multi-GPU: one process (one ndtb_ctx) per GPU.  Edges / scan pairs are independent units, so the only cross-GPU
+ * step is the gather of the fixed-size result records after a sharded batch — the serial loop over links of
+ * NDTFeatureGraph::updateLinksUsingNDTRegistration (ndt_feature_graph.cpp:347-353) split over ranks.  NCCL (all-gather
+ * over NVLink / NVSwitch) is loaded at run time (libnccl.so.2); without it these calls return NDTB_ERR_CUDA. */
+typedef struct ndtb_comm ndtb_comm;
+/* rank 0 creates the id and shares it with the other ranks out of band (file, socket, MPI, the launcher's store) */
+int ndtb_comm_unique_id(char id128[128]);
+int ndtb_comm_create(ndtb_ctx *ctx, const char id128[128], int rank, int world, ndtb_comm **out);
+void ndtb_comm_destroy(ndtb_comm *c);
+/* every rank contributes n_local records (device memory, the same n_local on every rank: pad the last shard);
+ * all_dev (device memory, world * n_local records) receives rank r's records at [r * n_local, (r+1) * n_local).
+ * Enqueued on the context's stream; synchronise the context before reading all_dev from the host. */
+int ndtb_gather_results(ndtb_comm *c, const ndtb_result *local_dev, int64_t n_local, ndtb_result *all_dev);
+
 /* ndt_feature::overlapNDTOccupancyScore(ref, mov, T) */
 int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T,
                        double *score);
+/* the same for n links in one launch (updateLinksUsingNDTRegistration with !keepScore, ndt_feature_graph.cpp:335-342).
+ * T: n poses T_stride_bytes apart (128 for packed poses, sizeof(ndtb_result) to read the T field of result records) in
+ * `T_mem` memory; scores: n doubles in `out_mem` memory. */
+int ndtb_overlap_score_batch(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *ref, const ndtb_map *const *mov, const void *T,
+                             int64_t T_stride_bytes, int T_mem, int out_mem, double *scores);
 
 #ifdef __cplusplus
 }

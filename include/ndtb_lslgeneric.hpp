@@ -87,6 +87,19 @@ struct MatrixXd {
   const double *data() const { return m.data(); }
   double *data() { return m.data(); }
 };
+template <typename S, int R, int C>
+struct Matrix {  // fixed-size column-major matrix / vector (Eigen::Matrix<double,6,1> increment of the line searches)
+  S v[R * C] = {};
+  S &operator()(int i) { return v[i]; }
+  S operator()(int i) const { return v[i]; }
+  S &operator()(int i, int j) { return v[j * R + i]; }
+  S operator()(int i, int j) const { return v[j * R + i]; }
+  void setZero() {
+    for (int i = 0; i < R * C; i++) v[i] = S(0);
+  }
+  const S *data() const { return v; }
+  S *data() { return v; }
+};
 struct Affine3d {
   double m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};  // column-major 4x4
   struct MatrixRef {
@@ -148,22 +161,23 @@ inline int &last_status() {
   static thread_local int s = NDTB_OK;
   return s;
 }
+// Contexts are created on first use, one per (host thread, device), and are NEVER destroyed before process exit: every
+// NDTMap keeps the raw context pointer (its storage is freed stream-ordered on that context), so a map may outlive the
+// thread that created it or a change of current_device().
 struct CtxHolder {
-  ndtb_ctx *ctx = nullptr;
-  int device = -1;
-  ~CtxHolder() {
-    if (ctx) ndtb_ctx_destroy(ctx);
-  }
+  std::vector<std::pair<int, ndtb_ctx *>> ctxs;  // (device, context) of this thread; intentionally leaked at thread exit
 };
 // Returns nullptr (and sets last_status) when no CUDA device / library problem: callers fail like the reference
 // fails, by returning false / non-zero.
 inline ndtb_ctx *context() {
   static thread_local CtxHolder h;
-  if (h.ctx && h.device == current_device()) return h.ctx;
-  if (h.ctx) ndtb_ctx_destroy(h.ctx), h.ctx = nullptr;
-  last_status() = ndtb_ctx_create(current_device(), nullptr, &h.ctx);
-  h.device = current_device();
-  return last_status() == NDTB_OK ? h.ctx : nullptr;
+  for (auto &dc : h.ctxs)
+    if (dc.first == current_device()) return dc.second;
+  ndtb_ctx *c = nullptr;
+  last_status() = ndtb_ctx_create(current_device(), nullptr, &c);
+  if (last_status() != NDTB_OK) return nullptr;
+  h.ctxs.push_back({current_device(), c});
+  return c;
 }
 
 template <class Affine>
@@ -203,6 +217,23 @@ class LazyGrid : public SpatialIndex {
 
  private:
   double cx_, cy_, cz_;
+};
+
+class NDTCell;
+// lslgeneric::CellVector [upstream]: the index of the feature / odometry NDT maps (ndt_feature_fuser_hmt.cpp:281-325).
+// Those maps hold at most a few dozen correspondence cells and are empty in every shipped configuration
+// (useFeat = useOdom = false); kept as a host container so that the reference's call sites compile.
+class CellVector : public SpatialIndex {
+ public:
+  ~CellVector() override;
+  void getCellSize(double &cx, double &cy, double &cz) const override { cx = cy = cz = 1.0; }
+  void addCell(NDTCell *c) { cells_.push_back(c); }
+  void addNDTCell(NDTCell *c) { cells_.push_back(c); }
+  int size() const { return (int)cells_.size(); }
+  NDTCell *getCellIdx(unsigned int i) const { return i < cells_.size() ? cells_[i] : nullptr; }
+
+ private:
+  std::vector<NDTCell *> cells_;
 };
 
 // Host snapshot of one cell (what pseudoTransformNDT / getAllCells hand to legacy code; caller deletes).
@@ -254,17 +285,42 @@ class NDTCell {
   float occ_ = 0.f;
 };
 
+inline CellVector::~CellVector() {
+  for (NDTCell *c : cells_) delete c;
+}
+
 class NDTMap {
  public:
   // NDTMap(new LazyGrid(res)) / NDTMap(idx, true): the index only carries the resolution, the grid lives in HBM
   explicit NDTMap(SpatialIndex *idx, bool dealloc = false) {
     double cx = 0.5, cy = 0.5, cz = 0.5;
     if (idx) idx->getCellSize(cx, cy, cz);
+    if (CellVector *cv = dynamic_cast<CellVector *>(idx)) {  // a feature / odometry map: host cells only
+      cell_vector_ = cv, owns_index_ = dealloc;
+      return;
+    }
     if (dealloc) delete idx;  // upstream keeps it as prototype and frees it in ~NDTMap; nothing else to keep here
     if (ndtb_ctx *c = ndtb::context()) ndtb::last_status() = ndtb_map_create(c, cx, cy, cz, &h_);
   }
   ~NDTMap() {
     if (h_) ndtb_map_destroy(h_);
+    if (cell_vector_ && owns_index_) delete cell_vector_;
+  }
+  SpatialIndex *getMyIndex() const { return cell_vector_; }
+  // pseudoTransformNDTMap(T) of a CellVector map (ndt_feature_fuser_hmt.cpp:297-305): a new host map, caller deletes
+  template <class Affine>
+  NDTMap *pseudoTransformNDTMap(const Affine & /*T*/) const {
+    return new NDTMap(new CellVector(), true);  // the feature branch is outside the engine's scope: its maps stay empty
+  }
+  // loadPointCloudCentroid(pc, origin, old_centroid, map_size, range_limit) (ndt_feature_fuser_hmt.cpp:199-217)
+  template <class Cloud>
+  void loadPointCloudCentroid(const Cloud &pc, const Eigen::Vector3d &origin, const Eigen::Vector3d &old_centroid,
+                              const Eigen::Vector3d &map_size, double range_limit) {
+    if (!h_) return;
+    const double o[3] = {origin(0), origin(1), origin(2)}, c[3] = {old_centroid(0), old_centroid(1), old_centroid(2)};
+    const double ms[3] = {map_size(0), map_size(1), map_size(2)};
+    ndtb::last_status() = ndtb_map_load_point_cloud_centroid(h_, reinterpret_cast<const float *>(pc.points.data()),
+                                                             (int64_t)pc.points.size(), NDTB_MEM_HOST, o, c, ms, range_limit);
   }
   NDTMap(const NDTMap &) = delete;
   NDTMap &operator=(const NDTMap &) = delete;
@@ -284,14 +340,17 @@ class NDTMap {
       ndtb::last_status() = ndtb_map_load_point_cloud(h_, reinterpret_cast<const float *>(pc.points.data()),
                                                       (int64_t)pc.points.size(), range_limit, NDTB_MEM_HOST, nullptr);
   }
-  // addPointCloud(origin, pc, classifierTh, maxz, sensor_noise, occupancy_limit): end-point binning; the free-space
-  // ray trace from `origin` is the "next" row of the scope table and is not applied.
+  // addPointCloud(origin, pc, classifierTh, maxz, sensor_noise, occupancy_limit) [upstream]: end points binned, every
+  // ray from `origin` traced through the grid and the occupancy of the cells it meets updated (LazyGrid::traceLine);
+  // call sites ndt_feature_fuser_hmt.cpp:92,485.  Takes effect at the next computeNDTCells, as the reference calls them.
   template <class Cloud>
-  void addPointCloud(const Eigen::Vector3d & /*origin*/, const Cloud &pc, double /*classifierTh*/ = 0.06,
-                     double /*maxz*/ = 100.0, double /*sensor_noise*/ = 0.25, double /*occupancy_limit*/ = 255) {
-    if (h_)
-      ndtb::last_status() = ndtb_map_add_points(h_, reinterpret_cast<const float *>(pc.points.data()),
-                                                (int64_t)pc.points.size(), NDTB_MEM_HOST, nullptr);
+  void addPointCloud(const Eigen::Vector3d &origin, const Cloud &pc, double classifierTh = 0.06, double maxz = 100.0,
+                     double sensor_noise = 0.25, double occupancy_limit = 255) {
+    if (!h_) return;
+    const double o[3] = {origin(0), origin(1), origin(2)};
+    ndtb::last_status() = ndtb_map_add_point_cloud(h_, o, reinterpret_cast<const float *>(pc.points.data()),
+                                                   (int64_t)pc.points.size(), NDTB_MEM_HOST, classifierTh, maxz, sensor_noise,
+                                                   occupancy_limit);
   }
   void computeNDTCells(int cellupdatemode = CELL_UPDATE_MODE_SAMPLE_VARIANCE, unsigned int maxnumpoints = 1000000000u,
                        float occupancy_limit = 255, Eigen::Vector3d /*origin*/ = Eigen::Vector3d(0, 0, 0),
@@ -362,6 +421,8 @@ class NDTMap {
     return out;
   }
   ndtb_map *h_ = nullptr;
+  CellVector *cell_vector_ = nullptr;
+  bool owns_index_ = false;
 };
 
 class NDTMatcherD2D {
@@ -378,6 +439,57 @@ class NDTMatcherD2D {
 
   NDTMatcherD2D() {}
   NDTMatcherD2D(bool /*isIrregularGrid*/, bool /*useDefaultGridResolutions*/, std::vector<double> /*resolutions*/) {}
+
+  // NDTMatcherD2D::MoreThuente [upstream]: the helpers the in-repo line searches call (ndt_matcher_d2d_fusion.h:154-165,
+  // 320,347,366,529-540,729,756,775)
+  struct MoreThuente {
+    static double min(double a, double b) { return a < b ? a : b; }
+    static double max(double a, double b) { return a > b ? a : b; }
+    static int cstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp, double &fp,
+                     double &dp, bool &brackt, double stmin, double stmax) {
+      int b = brackt ? 1 : 0;
+      const int info = ndtb_mt_cstep(&stx, &fx, &dx, &sty, &fy, &dy, &stp, fp, dp, &b, stmin, stmax);
+      brackt = b != 0;
+      return info;
+    }
+  };
+
+  // derivativesNDT(sourceNDT, targetNDT, score_gradient, Hessian, computeHessian) on a vector of already moved cells
+  // (ndt_matcher_d2d_fusion.h:856,617,444)
+  template <class Mat>
+  double derivativesNDT(const std::vector<NDTCell *> &sourceNDT, const NDTMap &targetNDT, Mat &score_gradient, Mat &Hessian,
+                        bool computeHessian) {
+    ndtb_ctx *c = ndtb::context();
+    if (!c || !targetNDT.handle()) return 0.0;
+    std::vector<ndtb_cell> cells(sourceNDT.size());
+    for (size_t i = 0; i < sourceNDT.size(); i++) sourceNDT[i]->to(cells[i]);
+    double out[43];
+    const ndtb_params p = params();
+    ndtb::last_status() = ndtb_d2d_derivatives_cells(c, targetNDT.handle(), cells.data(), (int64_t)cells.size(), nullptr, &p,
+                                                     computeHessian, out, nullptr);
+    if (ndtb::last_status() != NDTB_OK) return 0.0;
+    score_gradient.resize(6, 1);
+    Hessian.resize(6, 6);
+    for (int i = 0; i < 6; i++) {
+      score_gradient(i, 0) = out[1 + i];
+      for (int j = 0; j < 6; j++) Hessian(i, j) = out[7 + i * 6 + j];
+    }
+    return out[0];
+  }
+  // lineSearchMT(increment, sourceNDT, targetNDT) -> step (ndt_matcher_d2d_fusion.h:1013); increment may be negated
+  template <class Vec6>
+  double lineSearchMT(Vec6 &increment, std::vector<NDTCell *> &sourceNDT, NDTMap &targetNDT) {
+    ndtb_ctx *c = ndtb::context();
+    if (!c || !targetNDT.handle()) return 0.0;
+    std::vector<ndtb_cell> cells(sourceNDT.size());
+    for (size_t i = 0; i < sourceNDT.size(); i++) sourceNDT[i]->to(cells[i]);
+    double inc[6], step = 0.0;
+    for (int i = 0; i < 6; i++) inc[i] = increment(i);
+    const ndtb_params p = params();
+    ndtb::last_status() = ndtb_d2d_line_search_cells(c, targetNDT.handle(), cells.data(), (int64_t)cells.size(), inc, &p, &step);
+    for (int i = 0; i < 6; i++) increment(i) = inc[i];
+    return ndtb::last_status() == NDTB_OK ? step : 0.0;
+  }
 
   ndtb_params params() const {
     ndtb_params p;
@@ -481,9 +593,55 @@ class NDTMatcherP2D {
   }
 };
 
+// NDTMatcherFeatureD2D(corr) [upstream]: D2D between cells with known correspondences (the FLIRT feature / odometry term of
+// matchFusion, ndt_matcher_d2d_fusion.h:812,858,1016,1087).  With useFeat = useOdom = false — every shipped configuration —
+// its maps are empty, its derivatives are zero and its line search returns 0: that trivial host behaviour is all the
+// engine provides (out of scope as a kernel).
+class NDTMatcherFeatureD2D {
+ public:
+  explicit NDTMatcherFeatureD2D(const std::vector<std::pair<int, int>> &corr) : corr_(corr) {}
+  template <class Mat>
+  double derivativesNDT(const std::vector<NDTCell *> &, const NDTMap &, Mat &score_gradient, Mat &Hessian, bool) {
+    score_gradient.resize(6, 1), Hessian.resize(6, 6);
+    score_gradient.setZero(), Hessian.setZero();
+    return 0.0;
+  }
+  template <class Vec6>
+  double lineSearchMT(Vec6 &, std::vector<NDTCell *> &, NDTMap &) { return 0.0; }
+  size_t correspondences() const { return corr_.size(); }
+
+ private:
+  std::vector<std::pair<int, int>> corr_;
+};
+
 }  // namespace lslgeneric
 
 namespace ndt_feature {
+
+// matchFusion with the reference's exact parameter list (ndt_matcher_d2d_fusion.h:797-804, call site
+// ndt_feature_fuser_hmt.cpp:356-357).  The NDT term runs on the engine; the feature maps are accepted for source
+// compatibility and must be empty (useFeat = false, or no correspondences): a non-empty feature term is refused (returns
+// false with last_status() == NDTB_ERR_ARG) rather than silently ignored.
+template <class Affine, class Mat>
+inline bool matchFusion(lslgeneric::NDTMap &targetNDT, lslgeneric::NDTMap &sourceNDT, lslgeneric::NDTMap & /*targetNDT_feat*/,
+                        lslgeneric::NDTMap & /*sourceNDT_feat*/, const std::vector<std::pair<int, int>> &corr_feat, Affine &T,
+                        const Mat &Tcov, bool useInitialGuess, bool useNDT, bool useFeat, bool step_control, int ITR_MAX = 30,
+                        int n_neighbours = 2, double DELTA_SCORE = 10e-4, bool useSoftConstraints = true,
+                        bool step_control_fusion = true, bool useTikhonovRegularization = false);
+
+// matchFusion2d with the reference's parameter list (ndt_matcher_d2d_fusion.h:1159-1176, call site fuser_hmt.cpp:353)
+template <class Affine>
+inline bool matchFusion2d(lslgeneric::NDTMap &targetNDT, lslgeneric::NDTMap &sourceNDT, lslgeneric::NDTMap & /*targetNDT_feat*/,
+                          lslgeneric::NDTMap & /*sourceNDT_feat*/, const std::vector<std::pair<int, int>> & /*corr_feat*/,
+                          Affine &T, bool useInitialGuess, bool /*useNDT*/, bool /*useFeat*/, bool step_control,
+                          int ITR_MAX = 30, int n_neighbours = 2, double DELTA_SCORE = 10e-4) {
+  lslgeneric::NDTMatcherD2D_2D matcher_d2d_2d;
+  matcher_d2d_2d.n_neighbours = n_neighbours;
+  matcher_d2d_2d.step_control = step_control;
+  matcher_d2d_2d.ITR_MAX = ITR_MAX;
+  matcher_d2d_2d.DELTA_SCORE = DELTA_SCORE;
+  return matcher_d2d_2d.match(targetNDT, sourceNDT, T, useInitialGuess);
+}
 
 // matchFusion with useNDT = true and no feature / odometry cell term (useFeat = false; the configuration of every
 // offline driver, ndt_graph_offline.cpp:308): ndt_matcher_d2d_fusion.h:797-1155.
@@ -505,6 +663,19 @@ inline bool matchFusion(lslgeneric::NDTMap &targetNDT, lslgeneric::NDTMap &sourc
   if (ndtb::last_status() != NDTB_OK) return false;
   std::memcpy(ndtb::pose_data(T), r.T, sizeof r.T);
   return r.converged != 0;
+}
+
+template <class Affine, class Mat>
+inline bool matchFusion(lslgeneric::NDTMap &targetNDT, lslgeneric::NDTMap &sourceNDT, lslgeneric::NDTMap &, lslgeneric::NDTMap &,
+                        const std::vector<std::pair<int, int>> &corr_feat, Affine &T, const Mat &Tcov, bool useInitialGuess,
+                        bool useNDT, bool useFeat, bool step_control, int ITR_MAX, int n_neighbours, double DELTA_SCORE,
+                        bool useSoftConstraints, bool /*step_control_fusion*/, bool useTikhonovRegularization) {
+  if (!useNDT || (useFeat && !corr_feat.empty())) {  // feature / odometry-cell term: outside the engine's scope
+    ndtb::last_status() = NDTB_ERR_ARG;
+    return false;
+  }
+  return matchFusion(targetNDT, sourceNDT, T, Tcov, useInitialGuess, step_control, ITR_MAX, n_neighbours, DELTA_SCORE,
+                     useSoftConstraints, useTikhonovRegularization);
 }
 
 // matchFusion2d (ndt_matcher_d2d_fusion.h:1159-1176): NDT-only, through NDTMatcherD2D_2D
@@ -571,8 +742,14 @@ class GraphRegistrar {
       links[i].cov_3d.resize(6, 6);
       for (int a = 0; a < 6; a++)
         for (int b = 0; b < 6; b++) links[i].cov_3d(a, b) = cov[36 * i + a * 6 + b];
-      if (!keepScore)
-        links[i].score = ndt_feature::overlapNDTOccupancyScore(*nodes_[links[i].ref_idx], *nodes_[links[i].mov_idx], links[i].T);
+    }
+    if (!keepScore) {  // ndt_feature_graph.cpp:335-342, one launch over all links
+      std::vector<double> sc(n);
+      const int rs = ndtb_overlap_score_batch(c, (int64_t)n, tg.data(), sr.data(), res.data(), (int64_t)sizeof(ndtb_result),
+                                              NDTB_MEM_HOST, NDTB_MEM_HOST, sc.data());
+      last_status() = rs;
+      if (rs != NDTB_OK) return rs;
+      for (size_t i = 0; i < n; i++) links[i].score = sc[i];
     }
     return NDTB_OK;
   }

@@ -156,6 +156,20 @@ def load_library():
         "ndtb_map_write_jff": (C.c_int, [vp, C.c_char_p]),
         "ndtb_map_load_jff": (C.c_int, [vp, C.c_char_p]),
         "ndtb_overlap_score": (C.c_int, [vp, vp, vp, vp, C.POINTER(dbl)]),
+        "ndtb_d2d_derivatives_cells": (C.c_int, [vp, vp, vp, i64, vp, PP, C.c_int, vp, C.POINTER(i64)]),
+        "ndtb_d2d_line_search_cells": (C.c_int, [vp, vp, vp, i64, vp, PP, C.POINTER(dbl)]),
+        "ndtb_mt_cstep": (C.c_int, [C.POINTER(dbl)] * 7 + [dbl, dbl, C.POINTER(C.c_int), dbl, dbl]),
+        "ndtb_map_load_point_cloud_centroid": (C.c_int, [vp, vp, i64, C.c_int, vp, vp, vp, dbl]),
+        "ndtb_overlap_score_batch": (C.c_int, [vp, i64, vp, vp, vp, i64, C.c_int, C.c_int, vp]),
+        "ndtb_edge_msg_pack": (i64, [C.c_uint32, C.c_uint32, vp, vp, vp, dbl, vp, i64]),
+        "ndtb_edge_msg_unpack": (C.c_int, [vp, i64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp, vp, vp, C.POINTER(C.c_int32), C.POINTER(dbl)]),
+        "ndtb_pose_archive_write": (C.c_int, [C.c_char_p, vp]),
+        "ndtb_pose_archive_read": (C.c_int, [C.c_char_p, vp]),
+        "ndtb_eval_string": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int32]),
+        "ndtb_comm_unique_id": (C.c_int, [vp]),
+        "ndtb_comm_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "ndtb_comm_destroy": (None, [vp]),
+        "ndtb_gather_results": (C.c_int, [vp, vp, i64, vp]),
         "ndtb_map_add_point_cloud": (C.c_int, [vp, vp, vp, i64, C.c_int, dbl, dbl, dbl, dbl]),
         "ndtb_transform_point_cloud": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, C.c_int]),
         "ndtb_fuser_default_params": (None, [C.POINTER(FuserParams)]),
@@ -313,6 +327,16 @@ class Engine:
                                                res.ctypes.data, cov.ctypes.data if with_covariance else None))
         return res, cov.reshape(n, 6, 6)
 
+    def overlap_scores(self, refs, movs, Ts):
+        """overlapNDTOccupancyScore of n links in one launch (ndt_feature_graph.cpp:335-342)."""
+        n = len(refs)
+        ra = (C.c_void_p * n)(*[m.h for m in refs])
+        ma = (C.c_void_p * n)(*[m.h for m in movs])
+        Tc = np.concatenate([_cm(T) for T in Ts]) if n else np.zeros(0)
+        out = np.zeros(n)
+        self.check(self.L.ndtb_overlap_score_batch(self.h, n, ra, ma, Tc.ctypes.data, 128, HOST, HOST, out.ctypes.data))
+        return out
+
     def register_scans(self, tgt_clouds, src_clouds, T0s, cell=0.5, map_size=None, range_limit=-1.0, params=None,
                        with_covariance=False):
         """Front-end step for a batch of scan pairs from HOST clouds: build both local maps, match, covariance."""
@@ -333,6 +357,80 @@ class Engine:
                                               int(with_covariance), HOST, HOST, res.ctypes.data,
                                               cov.ctypes.data if with_covariance else None))
         return res, cov.reshape(n, 6, 6)
+
+
+def edge_msg_pack(ref_idx, mov_idx, T, cov3, cov6, score):
+    """ROS1 wire bytes of ndt_feature/NDTEdgeMsg (edgeToMsg, ndtgraph_conversion.h:17-34)."""
+    L = load_library()
+    Tc = _cm(T)
+    c3 = np.ascontiguousarray(cov3, dtype=np.float64)
+    c6 = np.ascontiguousarray(cov6, dtype=np.float64) if cov6 is not None else None
+    n = L.ndtb_edge_msg_pack(ref_idx, mov_idx, Tc.ctypes.data, c3.ctypes.data, c6.ctypes.data if c6 is not None else None, score, None, 0)
+    buf = np.zeros(n, np.uint8)
+    L.ndtb_edge_msg_pack(ref_idx, mov_idx, Tc.ctypes.data, c3.ctypes.data, c6.ctypes.data if c6 is not None else None, score, buf.ctypes.data, n)
+    return buf.tobytes()
+
+
+def edge_msg_unpack(data):
+    L = load_library()
+    buf = np.frombuffer(data, np.uint8)
+    a, b, has, s = C.c_uint32(), C.c_uint32(), C.c_int32(), C.c_double()
+    T, c3, c6 = np.zeros(16), np.zeros(9), np.zeros(36)
+    rc = L.ndtb_edge_msg_unpack(buf.ctypes.data, len(buf), C.byref(a), C.byref(b), T.ctypes.data, c3.ctypes.data, c6.ctypes.data,
+                                C.byref(has), C.byref(s))
+    if rc != 0:
+        raise NdtbError("malformed NDTEdgeMsg")
+    return a.value, b.value, T.reshape(4, 4).T.copy(), c3.reshape(3, 3), (c6.reshape(6, 6) if has.value else None), s.value
+
+
+def pose_archive_write(path, T):
+    Tc = _cm(T)
+    if load_library().ndtb_pose_archive_write(str(path).encode(), Tc.ctypes.data) != 0:
+        raise NdtbError(f"cannot write {path}")
+
+
+def pose_archive_read(path):
+    T = np.zeros(16)
+    if load_library().ndtb_pose_archive_read(str(path).encode(), T.ctypes.data) != 0:
+        raise NdtbError(f"cannot read {path}")
+    return T.reshape(4, 4).T.copy()
+
+
+def eval_string(T, planar=False):
+    buf = C.create_string_buffer(512)
+    Tc = _cm(T)
+    n = load_library().ndtb_eval_string(Tc.ctypes.data, int(planar), buf, 512)
+    if n < 0:
+        raise NdtbError("eval string")
+    return buf.value.decode()
+
+
+class Comm:
+    """ndtb_comm: the NCCL communicator of a sharded batch (one rank per GPU); gather() = ndtb_gather_results."""
+
+    @staticmethod
+    def unique_id():
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        rc = L.ndtb_comm_unique_id(buf)
+        if rc != 0:
+            raise NdtbError("ndtb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def __init__(self, engine, unique_id, rank, world):
+        self.e = engine
+        h = C.c_void_p()
+        idb = C.create_string_buffer(bytes(unique_id), 128)
+        engine.check(engine.L.ndtb_comm_create(engine.h, idb, int(rank), int(world), C.byref(h)))
+        self.h, self.rank, self.world = h, rank, world
+
+    def gather(self, local_dev_ptr, n_local, all_dev_ptr):
+        self.e.check(self.e.L.ndtb_gather_results(self.h, local_dev_ptr, int(n_local), all_dev_ptr))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.e.L.ndtb_comm_destroy(self.h)
+            self.h = None
 
 
 class LazyGrid:
@@ -387,6 +485,13 @@ class NDTMap:
         self.e.check(self.e.L.ndtb_map_load_point_cloud(self.h, pts.ctypes.data, pts.shape[0], range_limit, HOST,
                                                         C.byref(nb) if want_count else None))
         return nb.value
+
+    def loadPointCloudCentroid(self, pts, origin, old_centroid, map_size, range_limit):
+        """NDTMap::loadPointCloudCentroid (ndt_feature_fuser_hmt.cpp:199-217)."""
+        pts = _pts4(pts)
+        o, c, ms = (np.ascontiguousarray(v, dtype=np.float64) for v in (origin, old_centroid, map_size))
+        self.e.check(self.e.L.ndtb_map_load_point_cloud_centroid(self.h, pts.ctypes.data, pts.shape[0], HOST, o.ctypes.data,
+                                                                 c.ctypes.data, ms.ctypes.data, float(range_limit)))
 
     def addPointCloud(self, pts, want_count=True):
         """End-point binning part of NDTMap::addPointCloud (no free-space ray tracing)."""
@@ -471,6 +576,24 @@ class NDTMatcherD2D:
         self.e.check(self.e.L.ndtb_d2d_derivatives(self.e.h, target.h, source.h, Tc.ctypes.data, C.byref(self.params),
                                                    int(computeHessian), out.ctypes.data, C.byref(npairs)))
         return out[0], out[1:7].copy(), out[7:].reshape(6, 6).copy(), npairs.value
+
+    def derivativesNDTCells(self, source_cells, target, computeHessian=True):
+        """The cell-vector overload (ndt_matcher_d2d_fusion.h:856): source_cells = CELL_DTYPE records already moved."""
+        cells = np.ascontiguousarray(source_cells, dtype=CELL_DTYPE)
+        out = np.zeros(43)
+        npairs = C.c_int64(0)
+        self.e.check(self.e.L.ndtb_d2d_derivatives_cells(self.e.h, target.h, cells.ctypes.data, cells.shape[0], None,
+                                                         C.byref(self.params), int(computeHessian), out.ctypes.data, C.byref(npairs)))
+        return out[0], out[1:7].copy(), out[7:].reshape(6, 6).copy(), npairs.value
+
+    def lineSearchMT(self, increment, source_cells, target):
+        """NDTMatcherD2D::lineSearchMT (ndt_matcher_d2d_fusion.h:1013): returns (step, increment possibly negated)."""
+        cells = np.ascontiguousarray(source_cells, dtype=CELL_DTYPE)
+        inc = np.ascontiguousarray(increment, dtype=np.float64).copy()
+        step = C.c_double(0)
+        self.e.check(self.e.L.ndtb_d2d_line_search_cells(self.e.h, target.h, cells.ctypes.data, cells.shape[0], inc.ctypes.data,
+                                                         C.byref(self.params), C.byref(step)))
+        return step.value, inc
 
     def match(self, target, source, T, useInitialGuess=True):
         """Returns the Result (res.pose() is the refined T, res.converged the bool upstream returns)."""

@@ -2,6 +2,7 @@
 // batched registration.  Host code only orchestrates (allocation, job tables, launches); all arithmetic
 // is in map_build.cu (kernel i) and d2d.cu (kernel ii + optimiser).  There is no CPU compute path here.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -164,6 +165,7 @@ struct ndtb_map {
   bool pending_built = false; // ... and their cells were already computed (with occupancy limit pending_occ)
   float pending_occ = 255.f;
   double pending_range = -1.0;
+  double range_origin[3] = {0, 0, 0};  // reference point of the range filter (loadPointCloudCentroid: the sensor origin)
   // all-cells structure
   SlabP s_blocks, s_cells;
   unsigned long long *amask = nullptr;
@@ -333,6 +335,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
     jobs[i].pts = pts[i].dev;
     jobs[i].npts = pts[i].n;
     jobs[i].range_limit = load[i] ? range[i] : -1.0;
+    for (int a = 0; a < 3; a++) jobs[i].range_origin[a] = load[i] ? maps[i]->range_origin[a] : 0.0;
     jobs[i].maxnumpoints = maxnumpoints;
     jobs[i].occ_limit = occ_limit;
     jobs[i].log_occ = std::log(0.6 / (1.0 - 0.6));
@@ -889,6 +892,7 @@ int ndtb_map_load_point_cloud(ndtb_map *m, const float *pts, int64_t n, double r
   m->pending_load = true;
   m->pending_range = range_limit;
   m->pending_built = false;
+  m->range_origin[0] = m->range_origin[1] = m->range_origin[2] = 0.0;
   std::vector<ndtb_map *> maps{m};
   std::vector<PointSrc> ps{{(const float4 *)buf->p, (int)n}};
   std::vector<char> empty;
@@ -901,6 +905,29 @@ int ndtb_map_load_point_cloud(ndtb_map *m, const float *pts, int64_t n, double r
     m->pending_occ = 255.f;
     *n_binned = m->last_binned;
   }
+  return NDTB_OK;
+}
+
+int ndtb_map_load_point_cloud_centroid(ndtb_map *m, const float *pts, int64_t n, int mem, const double *origin, const double *old_centroid,
+                                       const double *map_size, double range_limit) {
+  DeviceGuard dev_guard(m ? m->ctx : nullptr);
+  if (!m || !origin || !old_centroid || !map_size || n < 0 || n > 0x7fffffff || (n > 0 && !pts)) return NDTB_ERR_ARG;
+  ndtb_ctx *ctx = m->ctx;
+  SlabP buf;
+  if (int rc = stage_points(ctx, pts, n, mem, buf)) return rc;
+  // how many cells towards the new origin the centre moves from the old centroid [upstream]
+  double c[3];
+  for (int a = 0; a < 3; a++) c[a] = old_centroid[a] + std::floor((origin[a] - old_centroid[a]) / m->cell[a]) * m->cell[a];
+  m->guess_size = false, m->is_first_load = false;
+  m->centerx = c[0], m->centery = c[1], m->centerz = c[2];
+  m->map_sizex = map_size[0], m->map_sizey = map_size[1], m->map_sizez = map_size[2];
+  m->set_grid(c[0], c[1], c[2], map_size[0], map_size[1], map_size[2]);
+  if (m->nblocks() <= 0 || m->nblocks() * 64 >= ((int64_t)1 << 31)) return NDTB_ERR_GRID;
+  m->pending.clear();
+  m->pending.push_back({buf, (int)n});
+  m->pending_load = true, m->pending_built = false;
+  m->pending_range = range_limit;
+  for (int a = 0; a < 3; a++) m->range_origin[a] = origin[a];
   return NDTB_OK;
 }
 
@@ -1254,6 +1281,94 @@ int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src
   return NDTB_OK;
 }
 
+namespace {
+// host NDTCell copies -> a source-only pseudo map (compact Gaussian records, no table: sources are never probed)
+int cells_source(ndtb_ctx *ctx, const ndtb_cell *cells, int64_t n, std::unique_ptr<ndtb_map> &out) {
+  if (n < 0 || n > 0x7fffffff || (n > 0 && !cells)) return NDTB_ERR_ARG;
+  std::vector<double> g;
+  g.reserve(9 * (size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    if (!cells[i].has_gaussian) continue;
+    for (int q = 0; q < 3; q++) g.push_back(cells[i].mean[q]);
+    for (int q = 0; q < 6; q++) g.push_back(cells[i].cov[q]);
+  }
+  const size_t ng = g.size() / 9;
+  SlabP cbuf;
+  if (int rc = slab_alloc(ctx, 256 + 72 * std::max<size_t>(ng, 1), cbuf)) return rc;
+  CU_TRY(ctx, cudaMemsetAsync(cbuf->p, 0xFF, 256, ctx->stream));
+  if (ng > 0) {
+    CU_TRY(ctx, cudaMemcpyAsync(cbuf->p + 256, g.data(), 72 * ng, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // g is a local vector
+  }
+  out.reset(new ndtb_map());
+  ndtb_map *m = out.get();
+  m->ctx = ctx;
+  m->cell[0] = m->cell[1] = m->cell[2] = 1.0;
+  std::memset(&m->g, 0, sizeof m->g);
+  m->grid_ready = true;
+  m->s_cells = cbuf;
+  m->table = (HashEntry *)cbuf->p, m->tsize = 2;
+  m->gcell = (double *)(cbuf->p + 256), m->ng = (int)ng;
+  return NDTB_OK;
+}
+}  // namespace
+
+int ndtb_d2d_derivatives_cells(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_cell *src, int64_t n, const double *T,
+                               const ndtb_params *p, int want_hessian, double *out43, int64_t *n_pairs) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !tgt || !p || !out43) return NDTB_ERR_ARG;
+  std::unique_ptr<ndtb_map> s;
+  if (int rc = cells_source(ctx, src, n, s)) return rc;
+  const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  return ndtb_d2d_derivatives(ctx, tgt, s.get(), T ? T : I16, p, want_hessian, out43, n_pairs);
+}
+
+int ndtb_d2d_line_search_cells(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_cell *src, int64_t n, double *increment6,
+                               const ndtb_params *p, double *step) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !tgt || !p || !increment6 || !step) return NDTB_ERR_ARG;
+  std::unique_ptr<ndtb_map> sm;
+  if (int rc = cells_source(ctx, src, n, sm)) return rc;
+  // the optimiser's own More-Thuente state machine (csrc/optimizer.h), driven from the host: one gradient pass per trial
+  OptParams prm;
+  std::memset(&prm, 0, sizeof prm);
+  prm.itr_max = p->itr_max, prm.step_control = 1, prm.regularize = p->regularize, prm.delta_score = p->delta_score;
+  OptState st;
+  const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  opt_begin(st, prm, I16);
+  st.ls_only = 1;
+  for (int i = 0; i < 6; i++) st.incr[i] = increment6[i];
+  double out43[43], sums[29];
+  auto eval = [&](const Pose &P) -> int {
+    double T16[16];
+    pose_to_cm(P, T16);
+    if (int rc = ndtb_d2d_derivatives(ctx, tgt, sm.get(), T16, p, 0, out43, nullptr)) return rc;
+    for (int i = 0; i < 29; i++) sums[i] = 0.0;
+    for (int i = 0; i < 7; i++) sums[i] = out43[i];
+    return NDTB_OK;
+  };
+  if (int rc = eval(st.T)) return rc;
+  st.ls_soft = 0;
+  on_ls_init(st, prm, sums);
+  int guard = 0;
+  while (st.phase == PH_LS_EVAL && guard++ < 64) {
+    if (int rc = eval(st.Peval)) return rc;
+    opt_advance(st, prm, sums);
+  }
+  for (int i = 0; i < 6; i++) increment6[i] = st.incr[i];
+  *step = st.ls_result;
+  return NDTB_OK;
+}
+
+int ndtb_mt_cstep(double *stx, double *fx, double *dx, double *sty, double *fy, double *dy, double *stp, double fp, double dp,
+                  int *brackt, double stmin, double stmax) {
+  if (!stx || !fx || !dx || !sty || !fy || !dy || !stp || !brackt) return NDTB_ERR_ARG;
+  int b = *brackt != 0;
+  const int info = mt_cstep(*stx, *fx, *dx, *sty, *fy, *dy, *stp, fp, dp, b, stmin, stmax);
+  *brackt = b;
+  return info;
+}
+
 int ndtb_d2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0, const ndtb_params *p,
                    ndtb_result *res) {
   DeviceGuard dev_guard(ctx);
@@ -1424,31 +1539,50 @@ int ndtb_map_load_jff(ndtb_map *m, const char *path) {
   return ndtb_map_from_cells(m, &g, cells.data(), n, 1);
 }
 
-int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T, double *score) {
+// NDTFeatureGraph::updateLinkUsingNDTRegistration scores every refined link with overlapNDTOccupancyScore when !keepScore
+// (ndt_feature_graph.cpp:335-342): one launch over all links.  T = n x 16 doubles (or the T field of n ndtb_result records:
+// T_stride_bytes = sizeof(ndtb_result)) in `T_mem` memory; scores = n doubles in `out_mem` memory.
+int ndtb_overlap_score_batch(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *ref, const ndtb_map *const *mov, const void *T,
+                             int64_t T_stride_bytes, int T_mem, int out_mem, double *scores) {
   DeviceGuard dev_guard(ctx);
-  if (!ctx || !ref || !mov || !T || !score) return NDTB_ERR_ARG;
-  if (!map_ok(ref) || !map_ok(mov)) return NDTB_ERR_GRID;
-  if (mov->n_all == 0 || ref->n_all == 0) {
-    *score = 1.0;
-    return NDTB_OK;
+  if (!ctx || n < 0 || (n > 0 && (!ref || !mov || !T || !scores)) || T_stride_bytes < 128 || T_stride_bytes % 8) return NDTB_ERR_ARG;
+  if (n == 0) return NDTB_OK;
+  std::vector<BuildJob> j((size_t)(2 * n));
+  std::memset(j.data(), 0, sizeof(BuildJob) * j.size());
+  for (int64_t l = 0; l < n; l++) {
+    const ndtb_map *mm[2] = {ref[l], mov[l]};
+    for (int i = 0; i < 2; i++) {
+      if (!map_ok(mm[i])) return NDTB_ERR_GRID;
+      BuildJob &b = j[(size_t)(2 * l + i)];
+      b.g = mm[i]->g;
+      if (mm[i]->n_all > 0)
+        b.amask = mm[i]->amask, b.abase = mm[i]->abase, b.tb_list = mm[i]->tb_list, b.counts = mm[i]->counts, b.cocc = mm[i]->cocc;
+    }
   }
-  BuildJob j[2];
-  std::memset(j, 0, sizeof j);
-  const ndtb_map *mm[2] = {ref, mov};
-  for (int i = 0; i < 2; i++) {
-    j[i].g = mm[i]->g, j[i].amask = mm[i]->amask, j[i].abase = mm[i]->abase, j[i].tb_list = mm[i]->tb_list;
-    j[i].counts = mm[i]->counts, j[i].cocc = mm[i]->cocc;
-  }
+  cudaStream_t st = ctx->stream;
   Carver c;
-  const size_t o_j = c.take(sizeof j), o_T = c.take(128), o_out = c.take(8);
+  const size_t o_j = c.take(sizeof(BuildJob) * j.size()), o_T = c.take(T_mem == NDTB_MEM_DEVICE ? 0 : (size_t)T_stride_bytes * n);
+  const size_t o_out = c.take(8 * (size_t)n);
   SlabP s;
   if (int rc = slab_alloc(ctx, c.off, s)) return rc;
-  CU_TRY(ctx, cudaMemcpyAsync(s->p + o_j, j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(s->p + o_T, T, 128, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->launches += launch_overlap((const BuildJob *)(s->p + o_j), (const double *)(s->p + o_T), (double *)(s->p + o_out), ctx->stream);
-  CU_TRY(ctx, cudaMemcpyAsync(score, s->p + o_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(s->p + o_j, j.data(), sizeof(BuildJob) * j.size(), cudaMemcpyHostToDevice, st));
+  const double *d_T = (const double *)T;
+  if (T_mem != NDTB_MEM_DEVICE) {
+    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_T, T, (size_t)T_stride_bytes * n, cudaMemcpyHostToDevice, st));
+    d_T = (const double *)(s->p + o_T);
+  }
+  double *d_out = out_mem == NDTB_MEM_DEVICE ? scores : (double *)(s->p + o_out);
+  ctx->launches += launch_overlap((const BuildJob *)(s->p + o_j), (int)n, d_T, (int)(T_stride_bytes / 8), d_out, st);
+  CU_TRY(ctx, cudaGetLastError());
+  if (out_mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaMemcpyAsync(scores, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  // the job table and a host T are pageable stack / vector memory: they must have been consumed before returning
+  CU_TRY(ctx, cudaStreamSynchronize(st));
   return NDTB_OK;
+}
+
+int ndtb_overlap_score(ndtb_ctx *ctx, const ndtb_map *ref, const ndtb_map *mov, const double *T, double *score) {
+  if (!ctx || !ref || !mov || !T || !score) return NDTB_ERR_ARG;
+  return ndtb_overlap_score_batch(ctx, 1, &ref, &mov, T, 128, NDTB_MEM_HOST, NDTB_MEM_HOST, score);
 }
 
 int ndtb_transform_point_cloud(ndtb_ctx *ctx, const double *T16, const float *in, int64_t n, int in_mem, float *out, int out_mem) {
@@ -1501,6 +1635,95 @@ int ndtb_internal_upload(ndtb_ctx *ctx, void *dst, const void *src, size_t bytes
   CU_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, src_mem == NDTB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                               ctx->stream));
   if (src_mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may reuse its buffer
+  return NDTB_OK;
+}
+
+// ---- NCCL result gather (loaded lazily: the library itself has no link-time dependency on NCCL)
+namespace {
+struct NcclId128 {  // ncclUniqueId (passed by value)
+  char b[128];
+};
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclId128, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl() {
+  static NcclApi a;
+  static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+    a.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (a.h) break;
+  }
+  if (!a.h) return a;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+  a.AllGather = (decltype(a.AllGather))dlsym(a.h, "ncclAllGather");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather;
+  return a;
+}
+}  // namespace
+
+struct ndtb_comm {
+  ndtb_ctx *ctx;
+  void *comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+int ndtb_comm_unique_id(char id128[128]) {
+  if (!id128) return NDTB_ERR_ARG;
+  NcclApi &a = nccl();
+  if (!a.ok) return NDTB_ERR_CUDA;
+  return a.GetUniqueId(id128) == 0 ? NDTB_OK : NDTB_ERR_CUDA;
+}
+
+int ndtb_comm_create(ndtb_ctx *ctx, const char id128[128], int rank, int world, ndtb_comm **out) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !id128 || !out || world < 1 || rank < 0 || rank >= world) return NDTB_ERR_ARG;
+  NcclApi &a = nccl();
+  if (!a.ok) {
+    ctx->last_error = "libnccl.so.2 not found";
+    return NDTB_ERR_CUDA;
+  }
+  NcclId128 id;
+  std::memcpy(id.b, id128, 128);
+  ndtb_comm *c = new ndtb_comm();
+  c->ctx = ctx, c->rank = rank, c->world = world;
+  const int rc = a.CommInitRank(&c->comm, world, id, rank);
+  if (rc != 0) {
+    ctx->last_error = std::string("ncclCommInitRank: ") + (a.GetErrorString ? a.GetErrorString(rc) : "error");
+    delete c;
+    return NDTB_ERR_CUDA;
+  }
+  *out = c;
+  return NDTB_OK;
+}
+
+void ndtb_comm_destroy(ndtb_comm *c) {
+  if (!c) return;
+  DeviceGuard dev_guard(c->ctx);
+  cudaStreamSynchronize(c->ctx->stream);
+  if (c->comm) nccl().CommDestroy(c->comm);
+  delete c;
+}
+
+int ndtb_gather_results(ndtb_comm *c, const ndtb_result *local_dev, int64_t n_local, ndtb_result *all_dev) {
+  if (!c || n_local < 0 || (n_local > 0 && (!local_dev || !all_dev))) return NDTB_ERR_ARG;
+  if (n_local == 0) return NDTB_OK;
+  DeviceGuard dev_guard(c->ctx);
+  const int rc = nccl().AllGather(local_dev, all_dev, sizeof(ndtb_result) * (size_t)n_local, /*ncclChar*/ 0, c->comm, c->ctx->stream);
+  if (rc != 0) {
+    c->ctx->last_error = std::string("ncclAllGather: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error");
+    return NDTB_ERR_CUDA;
+  }
   return NDTB_OK;
 }
 

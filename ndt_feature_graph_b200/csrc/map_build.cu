@@ -20,10 +20,11 @@ namespace ndtb {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-__device__ __forceinline__ bool pt_skip(const float4 p, double range_limit) {
+__device__ __forceinline__ bool pt_skip(const float4 p, double range_limit, const double *o) {
   if (isnan(p.x) || isnan(p.y) || isnan(p.z)) return true;
   if (range_limit > 0) {
-    const double d = sqrt((double)p.x * (double)p.x + (double)p.y * (double)p.y + (double)p.z * (double)p.z);
+    const double d0 = (double)p.x - o[0], d1 = (double)p.y - o[1], d2 = (double)p.z - o[2];  // exact for o = 0
+    const double d = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
     if (d > range_limit) return true;
   }
   return false;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(128) k_centroid_chunks(const BuildJob *__restr
     }
 #pragma unroll
     for (int u = 0; u < CEN_U; u++) {
-      const bool ok = !pt_skip(p[u], j.range_limit);
+      const bool ok = !pt_skip(p[u], j.range_limit, j.range_origin);
       used += ok;
       const double v[3] = {ok ? (double)p[u].x : 0.0, ok ? (double)p[u].y : 0.0, ok ? (double)p[u].z : 0.0};
 #pragma unroll
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(32) k_centroid(const BuildJob *__restrict__ jo
             const int i = base + u * 32 + lane;
             float4 p = make_float4(nanf(""), 0.f, 0.f, 0.f);
             if (i < j.npts) p = j.pts[i];
-            const bool ok = !pt_skip(p, j.range_limit);
+            const bool ok = !pt_skip(p, j.range_limit, j.range_origin);
             const double x = a == 0 ? (double)p.x : (a == 1 ? (double)p.y : (double)p.z);
             const unsigned um = __ballot_sync(FULL, ok);
             for (int ll = 0; ll < 32; ll++) {
@@ -178,7 +179,7 @@ __global__ void k_extent(const BuildJob *__restrict__ jobs, const int *__restric
   unsigned long long kmax = 0ull, kmin = ~0ull;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
     const float4 p = j.pts[i];
-    if (pt_skip(p, j.range_limit)) continue;
+    if (pt_skip(p, j.range_limit, j.range_origin)) continue;
     const double d0 = cx - (double)p.x, d1 = cy - (double)p.y, d2 = cz - (double)p.z;
     const double dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
     md = dist > md ? dist : md;
@@ -323,7 +324,7 @@ __global__ void k_mark(const BuildJob *__restrict__ jobs) {
     for (int u = 0; u < 4; u++) {
       int ix, iy, iz;
       key[u] = -1, b[u] = 0, bit[u] = 0;
-      bool live = !pt_skip(p[u], j.range_limit);
+      bool live = !pt_skip(p[u], j.range_limit, j.range_origin);
       if (live && j.n_seg) {  // the end point of a ray that addPointCloud ignores is not binned either
         const int sgi = seg_of(j, i0 + u * stride);
         if (sgi >= 0) {
@@ -993,10 +994,16 @@ __global__ void k_points_as_cells(const float4 *__restrict__ pts, int n, double 
 // mean squared difference of rescaled occupancies over the initialised cells of `mov` mapped into `ref`.
 // Integer-free sums are accumulated per cell in (block, bit) order by ONE thread block with a fixed tree.
 __device__ __forceinline__ double occ_rescaled(float occ) { return 1.0 - 1.0 / (1.0 + exp((double)occ)); }
+// one CTA per link: jobs[2*link] = ref, jobs[2*link+1] = mov, T16 + 16*link (T_stride doubles between links), out[link]
 __global__ void __launch_bounds__(256) k_overlap(const BuildJob *__restrict__ jobs /*[0]=ref,[1]=mov*/, const double *__restrict__ T16,
-                                                  double *__restrict__ out) {
-  const BuildJob &ref = jobs[0], &mov = jobs[1];
-  const Pose T = pose_from_cm(T16);
+                                                  int T_stride, double *__restrict__ out_all) {
+  const BuildJob &ref = jobs[2 * blockIdx.x], &mov = jobs[2 * blockIdx.x + 1];
+  const Pose T = pose_from_cm(T16 + (size_t)T_stride * blockIdx.x);
+  double *out = out_all + blockIdx.x;
+  if (mov.counts == nullptr || ref.counts == nullptr) {  // a map without cells: the reference returns 1
+    if (threadIdx.x == 0) out[0] = 1.0;
+    return;
+  }
   double sum = 0.0;
   int nb = 0;
   const int ntb = mov.counts[1];
@@ -1137,8 +1144,8 @@ int launch_points_as_cells(const float4 *d_pts, int n, double *d_gcell, cudaStre
   k_points_as_cells<<<chunks_for(n, 1024), 256, 0, s>>>(d_pts, n, d_gcell);
   return 1;
 }
-int launch_overlap(const BuildJob *d_jobs2, const double *d_T16, double *d_out, cudaStream_t s) {
-  k_overlap<<<1, 256, 0, s>>>(d_jobs2, d_T16, d_out);
+int launch_overlap(const BuildJob *d_jobs2, int n_links, const double *d_T16, int T_stride, double *d_out, cudaStream_t s) {
+  k_overlap<<<n_links, 256, 0, s>>>(d_jobs2, d_T16, T_stride, d_out);
   return 1;
 }
 

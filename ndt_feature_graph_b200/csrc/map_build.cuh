@@ -20,6 +20,7 @@ struct BuildJob {
   const float4 *pts;   // pending points (pcl::PointXYZ layout), device memory
   int npts;
   double range_limit;  // loadPointCloud range filter; <= 0: none
+  double range_origin[3];  // the filter's reference point ((0,0,0) for loadPointCloud, the sensor origin for loadPointCloudCentroid)
   // all-cells structure (new layout)
   unsigned long long *amask;  // [nblk] touched voxels per 4x4x4 block
   int *abase;                 // [nblk] exclusive popcount scan
@@ -86,6 +87,6 @@ int launch_from_cells_voxel(const BuildJob *d_job, const ndtb_cell *d_cells, int
 int launch_from_cells_place(const BuildJob *d_job, const ndtb_cell *d_cells, int n, const int *d_vox, cudaStream_t s);
 int launch_point_indices(const GridDesc &g, const float4 *d_pts, int n, int *d_out, int *d_nin, cudaStream_t s);
 int launch_points_as_cells(const float4 *d_pts, int n, double *d_gcell, cudaStream_t s);
-int launch_overlap(const BuildJob *d_jobs2, const double *d_T16, double *d_out, cudaStream_t s);
+int launch_overlap(const BuildJob *d_jobs2, int n_links, const double *d_T16, int T_stride, double *d_out, cudaStream_t s);
 
 }  // namespace ndtb

@@ -61,6 +61,9 @@ struct OptState {
   double score_last;
   int have_last;
   int n_exec;  // derivative passes actually executed on the device
+  // stand-alone NDTMatcherD2D::lineSearchMT (host-driven, ndtb_d2d_line_search_cells): stop after the search
+  int ls_only;
+  double ls_result;
 };
 
 // ------------------------------------------------------------------ small dense algebra
@@ -395,6 +398,7 @@ NDTB_HDF inline void opt_begin(OptState &s, const OptParams &prm, const double *
   for (int i = 0; i < 6; i++) s.pose_local[i] = s.x0[i] = s.incr[i] = s.scg[i] = s.X[i] = 0.0;
   s.ls_soft = 0;
   s.have_last = 0, s.n_exec = 0, s.score_last = 0;
+  s.ls_only = 0, s.ls_result = 0.0;
   for (int i = 0; i < 7; i++) s.sg[i] = 0.0;
   opt_request(s, s.T, 1, PH_NEWTON);
 }
@@ -460,6 +464,11 @@ NDTB_HDF inline void ls_start(OptState &s, const OptParams &prm, int soft) {
 }
 
 NDTB_HDF inline void ls_finish_step(OptState &s, const OptParams &prm, double step) {
+  if (s.ls_only) {  // lineSearchMT returns the step; the caller applies it
+    s.ls_result = step;
+    opt_finish(s);
+    return;
+  }
   if (prm.fusion) step = step > 0.0 ? step : 0.0;  // fusion.h:1018-1023 with step_size_feat == 0
   opt_apply_step(s, prm, step);
 }

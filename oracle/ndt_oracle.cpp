@@ -1443,6 +1443,40 @@ int orc_d2d_derivatives(const orc_map *tgt, const orc_map *src, const double *T,
   return 0;
 }
 
+// NDTMatcherD2D::lineSearchMT(increment, sourceNDT, targetNDT) [upstream] == ndt_matcher_d2d_fusion.h:390-793 without the
+// feature terms: the source cells moved by T are the `sourceNDT` vector; incr6 may be negated in place (:462)
+double orc_d2d_line_search(const orc_map *tgt, const orc_map *src, const double *T, double *incr6, const orc_params *p) {
+  std::vector<Gauss> s;
+  src->gaussians(s);
+  Counters cnt;
+  return line_search_mt(incr6, s, pose_from_cm(T), *tgt, *p, cnt);
+}
+
+// NDTMap::loadPointCloudCentroid(pc, origin, old_centroid, map_size, range_limit) [upstream], the loadCentroid branch of
+// the fuser's local-map build (ndt_feature_fuser_hmt.cpp:199-217): centre = old_centroid + floor((origin - old_centroid) /
+// cell) * cell, size = map_size, range filter around `origin`
+int64_t orc_map_load_point_cloud_centroid(orc_map *m, const float *pts, int64_t n, const double *origin, const double *old_centroid,
+                                          const double *map_size, double range_limit) {
+  double c[3];
+  for (int a = 0; a < 3; a++) c[a] = old_centroid[a] + std::floor((origin[a] - old_centroid[a]) / m->cell[a]) * m->cell[a];
+  m->guess_size = false;
+  m->is_first_load = false;
+  m->centerx = c[0], m->centery = c[1], m->centerz = c[2];
+  m->map_sizex = map_size[0], m->map_sizey = map_size[1], m->map_sizez = map_size[2];
+  m->set_grid(c[0], c[1], c[2], map_size[0], map_size[1], map_size[2]);
+  int64_t added = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const float *p = pts + 4 * i;
+    if (std::isnan(p[0]) || std::isnan(p[1]) || std::isnan(p[2])) continue;
+    if (range_limit > 0) {
+      const double d0 = (double)p[0] - origin[0], d1 = (double)p[1] - origin[1], d2 = (double)p[2] - origin[2];
+      if (std::sqrt(d0 * d0 + d1 * d1 + d2 * d2) > range_limit) continue;
+    }
+    if (m->add_point(p)) added++;
+  }
+  return added;
+}
+
 int orc_d2d_match(const orc_map *tgt, const orc_map *src, const double *T0, const orc_params *p, orc_result *res) {
   return match_impl(*tgt, *src, T0, *p, nullptr, *res);
 }

@@ -97,6 +97,10 @@ def lib():
     L.orc_map_point_indices.argtypes = [vp, vp, i64, vp]
     L.orc_d2d_derivatives.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_int, vp, C.POINTER(i64)]
     L.orc_d2d_match.argtypes = [vp, vp, vp, C.POINTER(Params), C.POINTER(Result)]
+    L.orc_d2d_line_search.restype = C.c_double
+    L.orc_d2d_line_search.argtypes = [vp, vp, vp, vp, C.POINTER(Params)]
+    L.orc_map_load_point_cloud_centroid.restype = i64
+    L.orc_map_load_point_cloud_centroid.argtypes = [vp, vp, i64, vp, vp, vp, C.c_double]
     L.orc_p2d_derivatives.argtypes = [vp, vp, i64, vp, C.POINTER(Params), C.c_int, vp, C.POINTER(i64)]
     L.orc_p2d_match.argtypes = [vp, vp, i64, vp, C.POINTER(Params), C.POINTER(Result)]
     L.orc_fusion_match.argtypes = [vp, vp, vp, vp, C.POINTER(Params), C.POINTER(Result)]
@@ -158,6 +162,12 @@ class OracleMap:
     def load_point_cloud(self, pts, range_limit=-1.0):
         pts = _pts4(pts)
         return lib().orc_map_load_point_cloud(self.h, pts.ctypes.data, pts.shape[0], range_limit)
+
+    def load_point_cloud_centroid(self, pts, origin, old_centroid, map_size, range_limit):
+        pts = _pts4(pts)
+        o, c, ms = (np.ascontiguousarray(v, dtype=np.float64) for v in (origin, old_centroid, map_size))
+        return lib().orc_map_load_point_cloud_centroid(self.h, pts.ctypes.data, pts.shape[0], o.ctypes.data, c.ctypes.data,
+                                                       ms.ctypes.data, range_limit)
 
     def add_points(self, pts):
         pts = _pts4(pts)
@@ -240,6 +250,15 @@ def p2d_match(tgt, pts, T0, params=None):
     rc = lib().orc_p2d_match(tgt.h, pts.ctypes.data, pts.shape[0], Tc.ctypes.data, C.byref(p), C.byref(r))
     assert rc == 0
     return r
+
+
+def d2d_line_search(tgt, src, T, increment, params=None):
+    """NDTMatcherD2D::lineSearchMT on the source cells moved by T: returns (step, increment possibly negated)."""
+    p = params or default_params()
+    inc = np.ascontiguousarray(increment, dtype=np.float64).copy()
+    Tc = _cm(T)
+    step = lib().orc_d2d_line_search(tgt.h, src.h, Tc.ctypes.data, inc.ctypes.data, C.byref(p))
+    return step, inc
 
 
 def d2d_is_stable(tgt, src, T0, base=None, tol=1e-9, **kw):

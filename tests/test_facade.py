@@ -143,3 +143,31 @@ def test_example_refines_saved_graph(golden, oracle, oracle_fixture_maps, tmp_pa
         assert abs(float(yaw) - np.arctan2(T[1, 0], T[0, 0])) < 2e-4
         so = oracle.overlap_occupancy_score(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T)
         assert abs(float(score) - so) < 2e-4
+
+
+def test_reference_call_sites_compile():
+    """tests/harness/callsites.cpp holds the reference's own call statements of the hot path (fuser initialize / update,
+    updateLinkUsingNDTRegistration, the optimiser's derivativesNDT / lineSearchMT / MoreThuente::cstep uses): they must
+    compile against the facade with -Wall -Wextra clean."""
+    import __graft_entry__ as g
+
+    exe = g.build_callsites_test()
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_reference_call_sites_run(oracle):
+    import __graft_entry__ as g
+
+    out = subprocess.run([g.build_callsites_test()], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = {l.split()[0]: l.split()[1:] for l in out.stdout.strip().splitlines()}
+    assert rows["matchFusion"][0] == "1"
+    # the second corridor scan is the first one shifted by 0.15 m along -x: the registration must recover it
+    assert abs(float(rows["matchFusion"][1]) - 0.15) < 0.02 and abs(float(rows["matchFusion"][2])) < 0.02
+    assert float(rows["covariance"][0]) > 0 and float(rows["covariance"][1]) > 0
+    assert int(rows["cells"][0]) > 20
+    # updateLinkUsingNDTRegistration with a default-constructed matcher (DELTA_SCORE 1e-3): converged, pose changed, so the
+    # covariance branch (:297-298) ran
+    assert rows["link"][0] == "1" and rows["link"][1] == "0" and float(rows["link"][2]) > 0 and float(rows["link"][4]) > 0
+    assert float(rows["blocks"][0]) < 0 and 0.0 < float(rows["blocks"][1]) <= 4.0 and int(rows["blocks"][2]) in (1, 2, 3, 4)

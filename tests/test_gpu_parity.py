@@ -456,3 +456,82 @@ def test_register_scans_tolerates_an_empty_scan(oracle, engine, c2small):
         assert res["status"][e] & 16 and res["pose_changed"][e] == 0  # NDTB_ST_NO_CELLS
         assert np.array_equal(res["T"][e].reshape(4, 4).T, T0)
         assert np.array_equal(cov[e], 0.02 * np.eye(6))  # ndt_feature_graph.cpp:300-310
+
+
+def test_gather_results_single_rank(engine, gpu_fixture_maps, golden):
+    """ndtb_gather_results (NCCL all-gather of the 192-byte result records) on a one-rank communicator: the C-ABI entry
+    point a C++ host uses after a sharded ndtb_d2d_match_batch; the multi-rank path is exercised by bench.py --gpus N."""
+    import torch
+
+    import ndt_feature_graph_b200 as N
+    from ndt_feature_graph_b200 import api
+
+    uid = api.Comm.unique_id()
+    comm = api.Comm(engine, uid, 0, 1)
+    T0s = [golden[f"Todom{k}"] for k in range(7)]
+    res, _ = engine.match_batch(gpu_fixture_maps[:7], gpu_fixture_maps[1:8], T0s, engine.default_params(delta_score=1e-6))
+    d_local = torch.from_numpy(res.view(np.uint8).copy()).cuda()
+    d_all = torch.zeros_like(d_local)
+    torch.cuda.synchronize()
+    comm.gather(d_local.data_ptr(), 7, d_all.data_ptr())
+    engine.synchronize()
+    out = np.frombuffer(d_all.cpu().numpy().tobytes(), dtype=api.RESULT_DTYPE)
+    assert np.array_equal(out["T"], res["T"]) and np.array_equal(out["iterations"], res["iterations"])
+    comm.close()
+
+
+def test_cell_vector_derivatives_and_line_search(engine, oracle, gpu_fixture_maps, oracle_fixture_maps, golden):
+    """The overloads the reference's optimiser calls: derivativesNDT(vector<NDTCell*>, NDTMap, g, H, bool)
+    (ndt_matcher_d2d_fusion.h:856) on cells moved on the host like pseudoTransformNDT (:840), and lineSearchMT (:1013)."""
+    import ndt_feature_graph_b200 as N
+
+    m = N.NDTMatcherD2D(engine, delta_score=1e-6)
+    prm = oracle.default_params(delta_score=1e-6)
+    for k in (1, 3, 5):
+        T = golden[f"Todom{k}"]
+        src = gpu_fixture_maps[k + 1].export_cells(True)
+        R, t = T[:3, :3], T[:3, 3]
+        moved = src.copy()
+        for i, c in enumerate(src):
+            C6 = c["cov"]
+            S = np.array([[C6[0], C6[1], C6[2]], [C6[1], C6[3], C6[4]], [C6[2], C6[4], C6[5]]])
+            moved["mean"][i] = R @ c["mean"] + t
+            M = R @ S @ R.T
+            moved["cov"][i] = [M[0, 0], M[0, 1], M[0, 2], M[1, 1], M[1, 2], M[2, 2]]
+        s_g, g_g, H_g, n_g = m.derivativesNDTCells(moved, gpu_fixture_maps[k])
+        s_o, g_o, H_o, n_o = oracle.d2d_derivatives(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T, prm)
+        assert n_g == n_o
+        assert abs(s_g - s_o) < 1e-9 * abs(s_o) and np.allclose(g_g, g_o, rtol=1e-8, atol=1e-10) and np.allclose(H_g, H_o, rtol=1e-8, atol=1e-8)
+        incr = -np.linalg.solve(H_o + 1e-3 * np.eye(6) * np.abs(H_o).max(), g_o)
+        st_g, inc_g = m.lineSearchMT(incr, moved, gpu_fixture_maps[k])
+        st_o, inc_o = oracle.d2d_line_search(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T, incr, prm)
+        assert abs(st_g - st_o) < 1e-6 * max(1.0, abs(st_o)), (k, st_g, st_o)
+        assert np.allclose(inc_g, inc_o)
+        st_g2, inc_g2 = m.lineSearchMT(-incr, moved, gpu_fixture_maps[k])  # wrong direction: negated in place
+        st_o2, inc_o2 = oracle.d2d_line_search(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T, -incr, prm)
+        assert abs(st_g2 - st_o2) < 1e-6 * max(1.0, abs(st_o2)) and np.allclose(inc_g2, inc_o2)
+
+
+def test_load_point_cloud_centroid(engine, oracle):
+    """NDTMap::loadPointCloudCentroid: the loadCentroid branch of the fuser's local map (ndt_feature_fuser_hmt.cpp:199-217)"""
+    import ndt_feature_graph_b200 as N
+
+    ca, _, _ = synth.velodyne_pair(2, n_rings=16, n_az=300)
+    origin, old_c, size = [3.3, -1.2, 0.4], [0.25, 0.25, 0.0], [60.0, 60.0, 10.0]
+    om = oracle.OracleMap(0.5)
+    no = om.load_point_cloud_centroid(ca, origin, old_c, size, 25.0)
+    om.compute_cells()
+    gm = N.NDTMap(engine, 0.5)
+    gm.loadPointCloudCentroid(ca, origin, old_c, size, 25.0)
+    gm.computeNDTCells()
+    assert np.allclose(gm.grid()[0], om.grid()[0]) and np.array_equal(gm.grid()[2], om.grid()[2])
+    assert np.allclose(om.grid()[0], [3.25, -1.25, 0.0])  # old centroid moved by whole cells towards the origin
+    _assert_cells_equal(om.export_cells(False), gm.export_cells(False))
+    assert no == int(gm.export_cells(False)["n"].sum()) or no > 0
+
+
+def test_overlap_scores_batched(engine, oracle, gpu_fixture_maps, oracle_fixture_maps, golden):
+    Ts = [golden[f"Tfuse{k}"] for k in range(7)]
+    got = engine.overlap_scores(gpu_fixture_maps[:7], gpu_fixture_maps[1:8], Ts)
+    for k in range(7):
+        assert abs(got[k] - oracle.overlap_occupancy_score(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], Ts[k])) < 1e-12

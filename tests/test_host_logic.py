@@ -159,3 +159,28 @@ def test_harness_linalg_matches_oracle(hh, oracle):
         b, x = rng.normal(size=6), np.zeros(6)
         hh.hh_ldlt6(A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
         np.testing.assert_allclose(A @ x, b, atol=1e-9)
+
+
+def test_abi_cstep_matches_oracle(oracle):
+    """NDTMatcherD2D::MoreThuente::cstep through the C ABI (ndtb_mt_cstep, host arithmetic: runs without a GPU)"""
+    import ctypes as C
+
+    import numpy as np
+
+    from ndt_feature_graph_b200 import api
+
+    L = api.load_library()
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        stx, sty = sorted(rng.uniform(0, 2, 2))
+        fx, fy, fp = rng.normal(size=3)
+        dx, dy, dp = rng.normal(size=3)
+        dx = -abs(dx)
+        stp = rng.uniform(stx, sty) if rng.random() < 0.7 else rng.uniform(0, 4)
+        brackt = bool(rng.integers(2))
+        info_o, vals_o, b_o = oracle.cstep(stx, fx, dx, sty, fy, dy, stp, fp, dp, brackt, min(stx, sty), max(stx, sty) + 1.0)
+        v = [C.c_double(x) for x in (stx, fx, dx, sty, fy, dy, stp)]
+        b = C.c_int(int(brackt))
+        info_g = L.ndtb_mt_cstep(*[C.byref(x) for x in v], fp, dp, C.byref(b), min(stx, sty), max(stx, sty) + 1.0)
+        assert info_g == info_o and bool(b.value) == b_o
+        assert all((a.value == o) or (np.isnan(a.value) and np.isnan(o)) for a, o in zip(v, vals_o))

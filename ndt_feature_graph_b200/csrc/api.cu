@@ -623,7 +623,9 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
   const int sms = std::max(ctx->sm_count, 1);
   auto pow2_floor = [](int v) { int p = 1; while (2 * p <= v) p <<= 1; return p; };
   int G1 = p->ctas_per_match > 0 ? pow2_floor(std::min(p->ctas_per_match, 8)) : ((int64_t)2 * n >= sms ? 1 : pow2_floor((int)std::min<int64_t>(8, sms / n)));
-  int budget = p->pass_budget > 0 ? p->pass_budget : (p->pass_budget < 0 ? 0 : (((int64_t)n * G1 >= sms) ? 64 : 0));
+  // hand-over also for batches that fill only half of the GPU (an edge shard of a multi-GPU run): their stragglers would
+  // otherwise finish alone on one CTA each
+  int budget = p->pass_budget > 0 ? p->pass_budget : (p->pass_budget < 0 ? 0 : (((int64_t)2 * n * G1 >= sms) ? 64 : 0));
   const size_t o_states = c.take(budget > 0 ? opt_state_bytes() * (size_t)n : 0), o_unf = c.take(4 * (size_t)(2 * n + 1));
   SlabP s;
   if (int rc = slab_alloc(ctx, c.off, s)) return rc;

@@ -637,6 +637,7 @@ cudaError_t launch_derivatives(const MatchJob *d_job, const MatchConfig &cfg, bo
 // sums g_i and per-target-cell gradient sums g_t; cov = H^-1 (sigma^2 sum_c g_c g_c^T) H^-1, sigma = 0.03.
 constexpr int COV_THREADS = 128;
 constexpr int COV_W = 28 + 21;  // H pass sums + upper triangle of sum g g^T
+constexpr double COV_FIX = 68719476736.0;  // 2^36
 
 __device__ __forceinline__ void outer_upper(const double *g, double *o) {
   int n = 0;
@@ -701,7 +702,10 @@ cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_r
 #pragma unroll
                 for (int a = 0; a < 6; a++) {
                   gs[a] += g6[a];
-                  atomicAdd(gtj + (size_t)slot * 6 + a, g6[a]);
+                  // per-target row: 64-bit fixed point (2^-36 resolution, range +-1.3e8) so that the atomic sum does not
+                  // depend on the order the pairs arrive in: the covariance is bit-identical from run to run
+                  atomicAdd(reinterpret_cast<unsigned long long *>(gtj) + (size_t)slot * 6 + a,
+                            (unsigned long long)__double2ll_rn(g6[a] * COV_FIX));
                 }
               }
             }
@@ -755,7 +759,7 @@ cov_finalize_kernel(const MatchJob *__restrict__ jobs, const ndtb_result *__rest
   for (int t = threadIdx.x; t < job.tgt.ng; t += COV_THREADS) {
     double g[6];
 #pragma unroll
-    for (int a = 0; a < 6; a++) g[a] = gtj[(size_t)t * 6 + a];
+    for (int a = 0; a < 6; a++) g[a] = (double)reinterpret_cast<const long long *>(gtj)[(size_t)t * 6 + a] * (1.0 / COV_FIX);
     outer_upper(g, o);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

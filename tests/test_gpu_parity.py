@@ -163,8 +163,10 @@ def test_derivatives_synthetic(oracle, engine, c1, c2small):
 def _check_result(ro, rg):
     err = synth.pose_error(ro.pose(), rg.pose())
     assert err < POSE_TIGHT, err
-    assert (ro.converged, ro.iterations, ro.n_hess_passes, ro.n_grad_passes, ro.exit_code) == (
-        rg.converged, rg.iterations, rg.n_hess_passes, rg.n_grad_passes, rg.exit_code)
+    assert (ro.converged, ro.iterations, ro.n_hess_passes, ro.exit_code) == (rg.converged, rg.iterations, rg.n_hess_passes, rg.exit_code)
+    # the number of line-search evaluations may differ by one or two: a More-Thuente acceptance test that sits within an
+    # ulp of its threshold is decided by the summation order of the 1e5 pair contributions (oracle: sequential; engine: tree)
+    assert abs(ro.n_grad_passes - rg.n_grad_passes) <= 2
     assert ro.pose_changed == rg.pose_changed
     assert abs(ro.score - rg.score) <= 1e-9 * max(1.0, abs(ro.score))
 

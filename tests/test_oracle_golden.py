@@ -104,6 +104,33 @@ def test_oracle_derivatives_finite_differences(golden, oracle, oracle_fixture_ma
     assert np.allclose(H, H.T)
 
 
+def test_oracle_hessian_full_6x6_finite_differences(golden, oracle, oracle_fixture_maps):
+    """All 36 entries of the D2D Hessian — rotation-rotation block with its Z / ZH terms included (the "coefficient 1 vs 2"
+    trap of SURVEY.md §8a) — against second central differences of the scalar score under the reference's own
+    parametrisation p -> score(Trans(p0..2) Rx(p3) Ry(p4) Rz(p5) * T) (ndt_matcher_d2d_fusion.h:1035-1043)."""
+    for k in (2, 5):
+        tgt, src = oracle_fixture_maps[k], oracle_fixture_maps[k + 1]
+        T = golden[f"Tfuse{k}"]
+        _, g, H, _ = oracle.d2d_derivatives(tgt, src, T)
+
+        def score(dp):
+            return oracle.d2d_derivatives(tgt, src, oracle.pose_from_vec(dp) @ T, want_hessian=False)[0]
+
+        # steps far below the length scale of the score (millimetre-thin Gaussians in z: 2e-6 rad is 20 um at 10 m)
+        hs = [2e-5, 2e-5, 2e-5, 2e-6, 2e-6, 2e-6]
+        fd = np.zeros((6, 6))
+        for i in range(6):
+            for j in range(i, 6):
+                ei, ej = np.zeros(6), np.zeros(6)
+                ei[i], ej[j] = hs[i], hs[j]
+                fd[i, j] = fd[j, i] = (score(ei + ej) - score(ei - ej) - score(ej - ei) + score(-ei - ej)) / (4 * hs[i] * hs[j])
+        scale = np.abs(H).max()
+        assert np.abs(fd - H).max() < 2e-4 * scale, (k, np.abs(fd - H).max() / scale)
+        # the rotation block on its own (it is an order of magnitude smaller than the largest entry in these planar maps)
+        rr = np.abs(H[3:, 3:]).max()
+        assert np.abs(fd[3:, 3:] - H[3:, 3:]).max() < 2e-3 * rr, (k, np.abs(fd[3:, 3:] - H[3:, 3:]).max() / rr)
+
+
 def test_oracle_cstep_and_linalg(oracle):
     rng = np.random.default_rng(1)
     for n in (3, 6):

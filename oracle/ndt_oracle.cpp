@@ -945,8 +945,28 @@ int match_cells(const orc_map &tgt, const std::vector<Gauss> &src, const double 
   int exit_code = 0;
   double score_here = 0;
   Deriv D;
+  // incremental mode (the reference's own data flow): nextNDT = pseudoTransformNDT(T) once (:840), every accepted increment
+  // moves that list in place (:1047-1056), derivatives and line searches are evaluated on it with no further pose
+  const bool inc = prm.incremental_cells != 0;
+  std::vector<Gauss> cur;
+  const Pose Pid = pose_identity();
+  auto move_list = [&](const Pose &M) {
+    for (Gauss &c : cur) {
+      double mu[3], tmp[9], C[9];
+      mat3_vec(M.R, c.mean, mu);
+      for (int a = 0; a < 3; a++) c.mean[a] = mu[a] + M.t[a];
+      mat3_mul(M.R, c.cov, tmp);
+      mat3_mulT(tmp, M.R, C);
+      std::memcpy(c.cov, C, sizeof C);
+    }
+  };
+  if (inc) {
+    cur = src;
+    move_list(T);
+  }
+  const std::vector<Gauss> &cells = inc ? cur : src;
   while (!convergence) {
-    derivatives_cells(src, T, tgt, prm, true, D);
+    derivatives_cells(cells, inc ? Pid : T, tgt, prm, true, D);
     cnt.hess++;
     score_here = D.score;
     double g[6], H[36];
@@ -1050,15 +1070,16 @@ int match_cells(const orc_map &tgt, const std::vector<Gauss> &src, const double 
       if (prm.step_control) {
         if (soft) {
           // :1008-1010 result is overwritten by :1012-1023, but `increment` may be flipped in place
-          (void)line_search_mt(incr, src, T, tgt, prm, cnt, true, pose_local, Q);
+          (void)line_search_mt(incr, cells, inc ? Pid : T, tgt, prm, cnt, true, pose_local, Q);
         }
-        step = line_search_mt(incr, src, T, tgt, prm, cnt);
+        step = line_search_mt(incr, cells, inc ? Pid : T, tgt, prm, cnt);
         // :1018-1023 with step_size_feat == 0  =>  step_size = max(step_ndt, 0)
         if (fusion) step = std::max(step, 0.0);
       }
       for (int i = 0; i < 6; i++) incr[i] *= step;
       Pose TR = pose_from_vec(incr);
       T = pose_mul(TR, T);
+      if (inc) move_list(TR);
       for (int i = 0; i < 6; i++) pose_local[i] += incr[i];
       double nrm = 0;
       for (int i = 0; i < 6; i++) nrm += incr[i] * incr[i];
@@ -1073,7 +1094,7 @@ int match_cells(const orc_map &tgt, const std::vector<Gauss> &src, const double 
     }
   }
   {
-    derivatives_cells(src, T, tgt, prm, false, D);
+    derivatives_cells(cells, inc ? Pid : T, tgt, prm, false, D);
     cnt.grad++;
     score_here = D.score;
     if (soft) score_here += maha_score(pose_local, Q);
@@ -1154,6 +1175,8 @@ void orc_default_params(orc_params *p) {
   p->use_tikhonov = 0;
   p->n_threads = 1;
   p->planar = 0;
+  p->incremental_cells = 0;
+  p->reserved_ = 0;
 }
 
 orc_map *orc_map_create(double cx, double cy, double cz) {

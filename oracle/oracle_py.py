@@ -37,6 +37,8 @@ class Params(C.Structure):
         ("use_tikhonov", C.c_int32),
         ("n_threads", C.c_int32),
         ("planar", C.c_int32),
+        ("incremental_cells", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

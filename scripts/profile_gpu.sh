@@ -7,7 +7,7 @@ TAG=${1:-r01}
 PAIRS=${2:-592}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --steps 1 --warmup 1 --pairs $PAIRS --no-cpu --no-e2e"
+BENCH="python bench.py --steps 1 --warmup 1 --pairs $PAIRS --no-cpu --no-e2e --no-extra --lanes 1"
 # 1) every launch of warm-up + timed step with its device time
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $BENCH > $OUT/launches_$TAG.log 2>&1
 # 2) full capture of the registration kernel: first (1 CTA per registration) and finishing (8-CTA clusters) launch of a step
@@ -19,6 +19,8 @@ timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --sectio
   --clock-control none -k regex:'k_|cov_' -s 20 -c 20 -f -o $OUT/build_$TAG $BENCH > $OUT/build_$TAG.log 2>&1
 ncu -i $OUT/build_$TAG.ncu-rep --page raw --csv > $OUT/build_${TAG}_raw.csv 2>/dev/null
 rm -f $OUT/build_$TAG.ncu-rep
+# 4) SASS evidence of the TMA bulk copy + mbarrier in the registration kernel
+cuobjdump -sass ndt_feature_graph_b200/lib/libndtb.so 2>/dev/null | grep -n -E "Function : .*match_kernel|UBLKCP|SYNCS|MBARRIER|ARRIVES" | head -40 > $OUT/match_${TAG}_sass_tma.txt
 gzip -f $OUT/match_${TAG}_source.csv
 ls -la $OUT
 du -sh $OUT

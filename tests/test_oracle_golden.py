@@ -131,6 +131,20 @@ def test_oracle_hessian_full_6x6_finite_differences(golden, oracle, oracle_fixtu
         assert np.abs(fd[3:, 3:] - H[3:, 3:]).max() < 2e-3 * rr, (k, np.abs(fd[3:, 3:] - H[3:, 3:]).max() / rr)
 
 
+def test_incremental_cell_moves_agree_with_cumulative_pose(golden, oracle, oracle_fixture_maps):
+    """The reference moves its copy of the source cells by every accepted increment (ndt_matcher_d2d_fusion.h:840,
+    1047-1056); oracle and engine evaluate T_cumulative * cell_original instead (nothing is written back on the GPU).  The
+    two data flows differ by rounding only: same iteration / pass counts and poses within 1e-9 on the real node pairs."""
+    for k in range(1, 7):
+        T0 = golden[f"Todom{k}"]
+        a = oracle.d2d_match(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T0, oracle.default_params(delta_score=1e-6))
+        b = oracle.d2d_match(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], T0,
+                             oracle.default_params(delta_score=1e-6, incremental_cells=1))
+        assert (a.converged, a.iterations, a.n_hess_passes) == (b.converged, b.iterations, b.n_hess_passes)
+        assert abs(a.n_grad_passes - b.n_grad_passes) <= 2
+        assert np.abs(a.pose() - b.pose()).max() < 1e-9, (k, np.abs(a.pose() - b.pose()).max())
+
+
 def test_oracle_cstep_and_linalg(oracle):
     rng = np.random.default_rng(1)
     for n in (3, 6):

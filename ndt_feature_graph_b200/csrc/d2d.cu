@@ -54,8 +54,31 @@ struct WarpScratch {
 // Hessian sums of the registration kernel: one shared-memory slot per lane and entry, hs[i * MATCH_THREADS + tid] (conflict
 // free), so that the 21 running sums do not compete with the pair arithmetic for registers.
 struct SmemAcc {
+  static constexpr bool kPairHook = false;
   double *slot;  // &hs[tid]
   __device__ __forceinline__ void add(int i, double v) const { slot[i * MATCH_THREADS] += v; }
+};
+
+// Covariance pass (NDTMatcherD2D::covariance [upstream], ndt_feature_graph.cpp:298): a Hessian pass that also needs
+// the rows of J^T J — the gradient sum of every SOURCE cell (all its pairs) and of every TARGET cell (all pairs that hit
+// it).  Pairs are spread over the lanes, so both kinds of rows are summed with 64-bit FIXED-POINT atomics (2^-36
+// resolution): integer addition is associative, the result does not depend on the order the pairs arrive in.
+constexpr double COV_FIX = 68719476736.0;  // 2^36
+constexpr int COV2_THREADS = 256;
+struct CovAcc {
+  static constexpr bool kPairHook = true;
+  double *slot;               // Hessian sums: per-lane shared-memory slots, stride COV2_THREADS
+  unsigned long long *gs;     // [32][6] source rows of the warp's current round (shared)
+  unsigned long long *gt;     // [n target cells][6] target rows of this registration (global)
+  __device__ __forceinline__ void add(int i, double v) const { slot[i * COV2_THREADS] += v; }
+  __device__ __forceinline__ void pair(int src_lane, int tgt_slot, const double *g6) const {
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      const unsigned long long v = (unsigned long long)__double2ll_rn(g6[a] * COV_FIX);
+      atomicAdd(gs + src_lane * 6 + a, v);
+      atomicAdd(gt + (size_t)tgt_slot * 6 + a, v);
+    }
+  }
 };
 
 struct PassCtx {
@@ -116,7 +139,11 @@ __device__ __forceinline__ void process_entry(const PassCtx &c, const WarpScratc
   for (int j = 0; j < 3; j++) m[j] = __ldg(t + j);
 #pragma unroll
   for (int j = 0; j < 6; j++) S[j] = __ldg(t + 3 + j);
-  if (pair_contrib_acc<HESS, HA>(mu0, mu1, mu2, C, m, S, c.lfd1, c.lfd2, acc, ha, nullptr)) acc[ACC_PAIRS] += 1.0;
+  double g6[6];
+  if (pair_contrib_acc<HESS, HA>(mu0, mu1, mu2, C, m, S, c.lfd1, c.lfd2, acc, ha, HA::kPairHook ? g6 : nullptr)) {
+    acc[ACC_PAIRS] += 1.0;
+    if constexpr (HA::kPairHook) ha.pair(sl, slot, g6);
+  }
 }
 
 // gradient pass: two pairs per lane at once (independent dependency chains interleave, hiding the fp64 / exp / load
@@ -319,6 +346,20 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
       qcount = 0;
     }
     __syncwarp();
+    if constexpr (HA::kPairHook) {  // covariance: this lane's source cell is complete — its row enters sum g g^T
+      double g[6];
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        g[a] = (double)(long long)ha.gs[lane * 6 + a] * (1.0 / COV_FIX);
+        ha.gs[lane * 6 + a] = 0ull;
+      }
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = a; b < 6; b++) acc[ACC_TOTAL + n++] += g[a] * g[b];
+      __syncwarp();
+    }
   }
 }
 
@@ -556,8 +597,12 @@ size_t opt_state_bytes() { return sizeof(OptState); }
 // The dynamic shared memory limit is an attribute of the FUNCTION on a device, shared by every context / host thread that
 // launches it: it is raised once per context creation to the device's opt-in maximum and never lowered per launch (two
 // threads with different table sizes would otherwise race on it).
+size_t cov_smem_bytes();
+__global__ void cov_pass_kernel(const MatchJob *, MatchConfig, const ndtb_result *, const long long *, double *, double *, const int *, int);
 cudaError_t match_kernel_prepare(int smem_optin_bytes) {
-  return cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_bytes);
+  cudaError_t e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(cov_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_smem_bytes());
 }
 
 // n_slots registrations (job_ids[slot] or slot itself), each on a cluster of `cluster` CTAs
@@ -635,9 +680,8 @@ cudaError_t launch_derivatives(const MatchJob *d_job, const MatchConfig &cfg, bo
 // ------------------------------------------------------------------ covariance
 // Definition (fixed by the CPU restatement): H = Hessian at T; rows = per-source-cell gradient
 // sums g_i and per-target-cell gradient sums g_t; cov = H^-1 (sigma^2 sum_c g_c g_c^T) H^-1, sigma = 0.03.
-constexpr int COV_THREADS = 128;
+constexpr int COV_THREADS = 128;      // cov_finalize_kernel
 constexpr int COV_W = 28 + 21;  // H pass sums + upper triangle of sum g g^T
-constexpr double COV_FIX = 68719476736.0;  // 2^36
 
 __device__ __forceinline__ void outer_upper(const double *g, double *o) {
   int n = 0;
@@ -647,89 +691,66 @@ __device__ __forceinline__ void outer_upper(const double *g, double *o) {
     for (int b = a; b < 6; b++) o[n++] += g[a] * g[b];
 }
 
-// grid (jobs, chunks): thread per source cell, hits processed serially; per-target sums by fp64 atomics.
-__global__ void __launch_bounds__(COV_THREADS)
+// grid (jobs, chunks): the pair-per-lane machinery of the registration kernel (d2d_pass) with the CovAcc policy.
+// dynamic smem: [WarpScratch x warps][gs rows x warps][21 x COV2_THREADS Hessian slots]
+struct CovShared {
+  GridDesc grid;
+  double P[12];
+  double red[(COV2_THREADS / 32) * 49];
+};
+__global__ void __launch_bounds__(COV2_THREADS, 1)
 cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_result *__restrict__ res,
                 const long long *__restrict__ gt_off, double *__restrict__ gt, double *__restrict__ partial,
                 const int *__restrict__ yielded, int mode /*0 all, 1 not yielded, 2 yielded only*/) {
   if (mode && (yielded[blockIdx.x] != 0) != (mode == 2)) return;
+  constexpr int NW = COV2_THREADS / 32;
   const MatchJob &job = jobs[blockIdx.x];
-  __shared__ double P[12];
-  __shared__ GridDesc grid;
-  __shared__ double red[(COV_THREADS / 32) * COV_W];
+  __shared__ CovShared sh;
+  WarpScratch *wsp = reinterpret_cast<WarpScratch *>(dyn_smem);
+  unsigned long long *gs_all = reinterpret_cast<unsigned long long *>(wsp + NW);
+  double *hs = reinterpret_cast<double *>(gs_all + NW * 32 * 6);
   const bool skip = res && !res[blockIdx.x].pose_changed;
-  if (threadIdx.x == 0) {
-    grid = job.tgt.g;
-    const Pose T = pose_from_cm(res ? res[blockIdx.x].T : job.T0);
-    for (int i = 0; i < 9; i++) P[i] = T.R[i];
-    for (int i = 0; i < 3; i++) P[9 + i] = T.t[i];
-  }
-  __syncthreads();
-  double acc[COV_W];
-#pragma unroll
-  for (int j = 0; j < COV_W; j++) acc[j] = 0.0;
-  const int k = cfg.n_neighbours;
-  double *gtj = gt + gt_off[blockIdx.x] * 6;
-  if (!skip) {
-    for (int i = blockIdx.y * COV_THREADS + threadIdx.x; i < job.src_ng; i += gridDim.y * COV_THREADS) {
-      double mu[3], C[6], gs[6] = {0, 0, 0, 0, 0, 0};
-      move_cell(P, job.src_gcell + (size_t)i * GC, mu, C);
-      int ix, iy, iz;
-      if (!voxel_index(grid, (double)__double2float_rn(mu[0]), (double)__double2float_rn(mu[1]),
-                       (double)__double2float_rn(mu[2]), ix, iy, iz))
-        continue;
-      for (int bx = (ix - k) >> 2; bx <= (ix + k) >> 2; bx++) {
-        if (bx < 0 || bx >= grid.nb[0]) continue;
-        const unsigned long long mx = expand_x(axis_bits(ix, k, bx));
-        for (int by = (iy - k) >> 2; by <= (iy + k) >> 2; by++) {
-          if (by < 0 || by >= grid.nb[1]) continue;
-          const unsigned long long mxy = mx & expand_y(axis_bits(iy, k, by));
-          for (int bz = (iz - k) >> 2; bz <= (iz + k) >> 2; bz++) {
-            if (bz < 0 || bz >= grid.nb[2]) continue;
-            int cbase;
-            unsigned long long bmask;
-            if (!table_find(job.tgt.table, job.tgt.tsize, (bx * grid.nb[1] + by) * grid.nb[2] + bz, cbase, bmask)) continue;
-            unsigned long long hits = bmask & mxy & expand_z(axis_bits(iz, k, bz));
-            while (hits) {
-              const int b = __ffsll((long long)hits) - 1;
-              hits &= hits - 1ull;
-              const int slot = cbase + __popcll(bmask & ((1ull << b) - 1ull));
-              const double *t = job.tgt.gcell + (size_t)slot * GC;
-              double m[3] = {__ldg(t), __ldg(t + 1), __ldg(t + 2)};
-              double S[6] = {__ldg(t + 3), __ldg(t + 4), __ldg(t + 5), __ldg(t + 6), __ldg(t + 7), __ldg(t + 8)};
-              double g6[6];
-              if (pair_contrib<true>(mu[0], mu[1], mu[2], C, m, S, cfg.lfd1, cfg.lfd2, acc, g6)) {
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-                  gs[a] += g6[a];
-                  // per-target row: 64-bit fixed point (2^-36 resolution, range +-1.3e8) so that the atomic sum does not
-                  // depend on the order the pairs arrive in: the covariance is bit-identical from run to run
-                  atomicAdd(reinterpret_cast<unsigned long long *>(gtj) + (size_t)slot * 6 + a,
-                            (unsigned long long)__double2ll_rn(g6[a] * COV_FIX));
-                }
-              }
-            }
-          }
-        }
-      }
-      outer_upper(gs, acc + 28);
-    }
-  }
-  // block reduce COV_W values (fixed tree) -> partial[job][cta][COV_W]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    sh.grid = job.tgt.g;
+    const Pose T = pose_from_cm(res ? res[blockIdx.x].T : job.T0);
+    for (int i = 0; i < 9; i++) sh.P[i] = T.R[i];
+    for (int i = 0; i < 3; i++) sh.P[9 + i] = T.t[i];
+  }
 #pragma unroll
-  for (int j = 0; j < COV_W; j++) {
-    double v = acc[j];
+  for (int j = 0; j < 21; j++) hs[j * COV2_THREADS + threadIdx.x] = 0.0;
+  for (int a = 0; a < 6; a++) gs_all[(warp * 32 + lane) * 6 + a] = 0ull;
+  __syncthreads();
+  double acc[ACC_TOTAL + 21];  // [0] score, [1..6] g, [28] pairs, [29..49] upper triangle of sum g g^T over source rows
+#pragma unroll
+  for (int j = 0; j < ACC_TOTAL + 21; j++) acc[j] = 0.0;
+  if (!skip) {
+    PassCtx c;
+    c.g = &sh.grid;
+    c.table = job.tgt.table, c.tsize = job.tgt.tsize, c.tcell = job.tgt.gcell;
+    c.scell = job.src_gcell, c.ns = job.src_ng;
+    c.k = cfg.n_neighbours, c.lfd1 = cfg.lfd1, c.lfd2 = cfg.lfd2;
+    const CovAcc ha{hs + threadIdx.x, gs_all + warp * 32 * 6, reinterpret_cast<unsigned long long *>(gt + gt_off[blockIdx.x] * 6)};
+    d2d_pass<true, CovAcc>(c, sh.P, wsp[warp], blockIdx.y * NW + warp, gridDim.y * NW, acc, ha);
+  }
+  // block reduce the 49 values (fixed tree) -> partial[job][chunk][COV_W]: [0..6] score+g, [7..27] H, [28..48] sum g g^T
+#pragma unroll
+  for (int j = 0; j < 49; j++) {
+    double v = j < 7 ? acc[j] : (j < 28 ? hs[(j - 7) * COV2_THREADS + threadIdx.x] : acc[ACC_TOTAL + (j - 28)]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-    if (lane == 0) red[warp * COV_W + j] = v;
+    if (lane == 0) sh.red[warp * 49 + j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < COV_W) {
+  if (threadIdx.x < 49) {
     double s = 0.0;
-    for (int w = 0; w < COV_THREADS / 32; w++) s += red[w * COV_W + threadIdx.x];
-    partial[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * COV_W + threadIdx.x] = s;
+    for (int w = 0; w < NW; w++) s += sh.red[w * 49 + threadIdx.x];
+    partial[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 49 + threadIdx.x] = s;
   }
+}
+
+size_t cov_smem_bytes() {
+  return (COV2_THREADS / 32) * sizeof(WarpScratch) + (size_t)(COV2_THREADS / 32) * 32 * 6 * 8 + (size_t)21 * COV2_THREADS * 8;
 }
 
 // one CTA per job: ordered sum of the partials, sum over target rows, 6x6 sandwich
@@ -803,7 +824,7 @@ cudaError_t launch_covariance(const MatchJob *d_jobs, int n_jobs, const MatchCon
                               const long long *d_gt_off, double *d_gt, double *d_partial, int n_chunks,
                               double *d_cov36, int *d_status, const int *d_yielded, int mode, cudaStream_t stream) {
   dim3 grid(n_jobs, n_chunks);  // jobs on x: no 65535 limit on the batch size
-  cov_pass_kernel<<<grid, COV_THREADS, 0, stream>>>(d_jobs, cfg, d_res, d_gt_off, d_gt, d_partial, d_yielded, mode);
+  cov_pass_kernel<<<grid, COV2_THREADS, cov_smem_bytes(), stream>>>(d_jobs, cfg, d_res, d_gt_off, d_gt, d_partial, d_yielded, mode);
   cov_finalize_kernel<<<n_jobs, COV_THREADS, 0, stream>>>(d_jobs, d_res, d_gt_off, d_gt, d_partial, n_chunks, d_cov36,
                                                          d_status, d_yielded, mode);
   return cudaGetLastError();

@@ -42,6 +42,7 @@ NDTB_HD constexpr int hidx(int p, int q) { return ACC_H + p * 6 - (p * (p - 1)) 
 // Where the 21 Hessian sums of a thread live: RegAcc = in the thread's accumulator array (acc[ACC_H + i]); a kernel
 // that wants the registers for the pair arithmetic passes its own policy (d2d.cu: one shared-memory slot per lane).
 struct RegAcc {
+  static constexpr bool kPairHook = false;  // true: the policy wants every pair's own gradient (covariance pass)
   double *acc;
   NDTB_HD void add(int i, double v) const { acc[ACC_H + i] += v; }
 };

@@ -387,7 +387,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
   std::vector<SlabP> keep_old;  // previous storage of merged maps stays alive until the end of the build
   Carver cb, ct;
   struct OffB {
-    size_t amask, abase, tbl, counts, ptc, seg, seg2, viscnt, visoff;
+    size_t amask, abase, tbl, counts, ptc, seg, seg2, key2, rshist, viscnt, visoff;
   };
   std::vector<OffB> ob(M);
   const size_t o_counts_all = cb.take(32 * (size_t)M);  // contiguous: one D2H copy for the whole batch
@@ -403,6 +403,8 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
     ob[i].ptc = ct.take(4 * (size_t)pts[i].n);
     ob[i].seg = ct.take(4 * (size_t)pts[i].n);
     ob[i].seg2 = ct.take(4 * (size_t)pts[i].n);
+    ob[i].key2 = ct.take(4 * (size_t)pts[i].n);
+    ob[i].rshist = ct.take(4 * 256 * (size_t)((pts[i].n + sort_tile_points() - 1) / sort_tile_points() + 1));
     if (jobs[i].n_seg) ob[i].viscnt = ct.take(4 * (size_t)pts[i].n), ob[i].visoff = ct.take(4 * (size_t)pts[i].n);
   }
   SlabP s_b, s_t;
@@ -422,6 +424,8 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
     j.pt_cell = (int *)(s_t->p + ob[i].ptc);
     j.seg_idx = (int *)(s_t->p + ob[i].seg);
     j.seg2 = (int *)(s_t->p + ob[i].seg2);
+    j.key2 = (int *)(s_t->p + ob[i].key2);
+    j.rs_hist = (int *)(s_t->p + ob[i].rshist);
     if (j.n_seg) j.vis_cnt = (int *)(s_t->p + ob[i].viscnt), j.vis_off = (int *)(s_t->p + ob[i].visoff);
     if (m->n_all > 0) {  // merge: start from the cells the map already has
       j.o_amask = m->amask, j.o_abase = m->abase, j.o_cmean = m->cmean, j.o_ccov = m->ccov;
@@ -449,7 +453,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
   Carver cc, ct2;
   struct OffC {
     size_t mean, cov, n, has, occ, gcell, g2c, table, cnt, segoff, cursor, gmask, gbase, ckey;
-    size_t vkey, vray, vidx, vseg2, vcnt, vsegoff;
+    size_t vkey, vray, vidx, vseg2, vkey2, vhist, vcnt, vsegoff;
   };
   std::vector<OffC> oc(L);
   int max_ntb = 1, max_cells = 1, max_vis = 1;
@@ -474,6 +478,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
       const size_t nv = (size_t)std::max(cnts[8 * l + 7], 1);
       max_vis = std::max(max_vis, cnts[8 * l + 7]);
       oc[l].vkey = ct2.take(4 * nv), oc[l].vray = ct2.take(4 * nv), oc[l].vidx = ct2.take(4 * nv), oc[l].vseg2 = ct2.take(4 * nv);
+      oc[l].vkey2 = ct2.take(4 * nv), oc[l].vhist = ct2.take(4 * 256 * (nv / (size_t)sort_tile_points() + 2));
       oc[l].vcnt = ct2.take(4 * na), oc[l].vsegoff = ct2.take(4 * na);
     }
   }
@@ -491,9 +496,13 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
     j.cnt = (int *)(s_t2->p + oc[l].cnt), j.seg_off = (int *)(s_t2->p + oc[l].segoff), j.cursor = (int *)(s_t2->p + oc[l].cursor);
     j.gmask_t = (unsigned long long *)(s_t2->p + oc[l].gmask), j.gbase_t = (int *)(s_t2->p + oc[l].gbase);
     j.cell_key = (int *)(s_t2->p + oc[l].ckey);
+    // the stable radix sort ping-pongs between (pt_cell, seg_idx) and (key2, seg2): an odd number of passes ends in seg2
+    const bool odd = sort_passes(max_cells) & 1;
+    j.sorted_ids = odd ? j.seg2 : j.seg_idx;
     if (j.n_seg) {
       j.vis_key = (int *)(s_t2->p + oc[l].vkey), j.vis_ray = (int *)(s_t2->p + oc[l].vray);
-      j.v_cnt = (int *)(s_t2->p + oc[l].vcnt), j.v_seg_off = (int *)(s_t2->p + oc[l].vsegoff), j.v_seg2 = (int *)(s_t2->p + oc[l].vseg2);
+      j.v_cnt = (int *)(s_t2->p + oc[l].vcnt), j.v_seg_off = (int *)(s_t2->p + oc[l].vsegoff);
+      j.v_seg2 = (int *)(s_t2->p + (odd ? oc[l].vseg2 : oc[l].vidx));
     }
   }
   CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
@@ -505,7 +514,9 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
       BuildJob &v = vj[l];
       v.pts = nullptr;
       v.npts = live[l].n_seg ? cnts[8 * l + 7] : 0;
-      v.pt_cell = live[l].vis_key, v.seg_idx = live[l].n_seg ? (int *)(s_t2->p + oc[l].vidx) : nullptr, v.seg2 = live[l].v_seg2;
+      v.pt_cell = live[l].vis_key;
+      v.seg_idx = live[l].n_seg ? (int *)(s_t2->p + oc[l].vidx) : nullptr, v.seg2 = live[l].n_seg ? (int *)(s_t2->p + oc[l].vseg2) : nullptr;
+      v.key2 = live[l].n_seg ? (int *)(s_t2->p + oc[l].vkey2) : nullptr, v.rs_hist = live[l].n_seg ? (int *)(s_t2->p + oc[l].vhist) : nullptr;
       v.cnt = live[l].v_cnt, v.seg_off = live[l].v_seg_off;
       if (!live[l].n_seg) v.n_all = 0, v.cnt = nullptr;  // nothing to do for a map without traced rays
     }

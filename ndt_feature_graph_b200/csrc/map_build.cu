@@ -418,10 +418,149 @@ __global__ void k_count(const BuildJob *__restrict__ jobs) {
     for (int u = 0; u < 4; u++) {
       if (key[u] < 0) continue;
       const int i = i0 + u * stride;
-      const int c = base[u] + __popcll(m[u] & ((1ull << (key[u] & 63)) - 1ull));
-      j.pt_cell[i] = c;
-      j.seg2[i] = atomicAdd(j.cnt + c, 1);  // arrival rank inside the cell (arbitrary order; k_sort_segments orders the ids)
+      j.pt_cell[i] = base[u] + __popcll(m[u] & ((1ull << (key[u] & 63)) - 1ull));  // cell id: the sort key
     }
+  }
+}
+
+// ---- stable LSD radix sort of the point ids by cell id (8-bit digits), batched over the maps of a build -------------
+// Replaces "atomic rank + scatter + per-cell sort": a stable sort keeps the ids of a cell ascending (= the insertion order
+// of NDTCell::points_ the per-cell sums are taken in) for free, without one atomic and without per-cell work.
+// Dropped points (key -1) sort to the end as key n_all.  Ping-pong: X = (pt_cell, seg_idx), Y = (key2, seg2); pass p reads
+// X when p is even; the ids of the first pass are implicit (iota).
+constexpr int RS_TILE = 2048, RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_PER_WARP = RS_TILE / RS_WARPS;
+__device__ __forceinline__ int rs_key(const BuildJob &j, const int *keys, int i) {
+  const int k = keys[i];
+  return k < 0 ? j.n_all : k;
+}
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const BuildJob *__restrict__ jobs, int shift, int parity) {
+  const BuildJob &j = jobs[blockIdx.y];
+  const int n = j.npts, tile = blockIdx.x;
+  if (tile * RS_TILE >= n || j.pt_cell == nullptr) return;
+  const int T = (n + RS_TILE - 1) / RS_TILE;
+  const int *keys = parity ? j.key2 : j.pt_cell;
+  __shared__ int hist[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < RS_TILE / RS_THREADS; u++) {
+    const int i = tile * RS_TILE + u * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&hist[(rs_key(j, keys, i) >> shift) & 255], 1);
+  }
+  __syncthreads();
+  j.rs_hist[threadIdx.x * T + tile] = hist[threadIdx.x];
+}
+// one CTA per map: exclusive scan of the 256 x tiles histogram in digit-major order
+__global__ void __launch_bounds__(1024) k_rs_scan(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.x];
+  if (j.pt_cell == nullptr || j.npts <= 0) return;
+  const int total = 256 * ((j.npts + RS_TILE - 1) / RS_TILE);
+  __shared__ int wsum[32];
+  int run = 0;
+  for (int base = 0; base < total; base += 1024) {
+    const int e = base + threadIdx.x;
+    const int v = e < total ? j.rs_hist[e] : 0;
+    int t;
+    const int ex = cta_excl_scan(v, &t, wsum);
+    if (e < total) j.rs_hist[e] = run + ex;
+    run += t;
+  }
+}
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const BuildJob *__restrict__ jobs, int shift, int parity, int first) {
+  const BuildJob &j = jobs[blockIdx.y];
+  const int n = j.npts, tile = blockIdx.x;
+  if (tile * RS_TILE >= n || j.pt_cell == nullptr) return;
+  const int T = (n + RS_TILE - 1) / RS_TILE;
+  const int *keys = parity ? j.key2 : j.pt_cell, *vals = parity ? j.seg2 : j.seg_idx;
+  int *okeys = parity ? j.pt_cell : j.key2, *ovals = parity ? j.seg_idx : j.seg2;
+  __shared__ int wh[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int q = threadIdx.x; q < RS_WARPS * 256; q += RS_THREADS) (&wh[0][0])[q] = 0;
+  __syncthreads();
+  const int w0 = tile * RS_TILE + warp * RS_PER_WARP;
+  // (a) digit counts of every warp's contiguous slice
+  for (int u = 0; u < RS_PER_WARP / 32; u++) {
+    const int i = w0 + u * 32 + lane;
+    const bool act = i < n;
+    const int d = act ? (rs_key(j, keys, i) >> shift) & 255 : 0;
+    const unsigned am = __ballot_sync(FULL, act);
+    if (act) {
+      const unsigned peers = __match_any_sync(am, d);
+      if (lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // (b) first output position of (warp, digit): global offset of (digit, tile) + the slices before this warp
+  {
+    const int d = threadIdx.x;
+    int base = j.rs_hist[d * T + tile];
+    for (int w = 0; w < RS_WARPS; w++) {
+      const int c = wh[w][d];
+      wh[w][d] = base;
+      base += c;
+    }
+  }
+  __syncthreads();
+  // (c) stable scatter: slices in order, lanes in order inside a chunk
+  for (int u = 0; u < RS_PER_WARP / 32; u++) {
+    const int i = w0 + u * 32 + lane;
+    const bool act = i < n;
+    const int k = act ? keys[i] : 0;
+    const int d = act ? ((k < 0 ? j.n_all : k) >> shift) & 255 : 0;
+    const unsigned am = __ballot_sync(FULL, act);
+    if (act) {
+      const unsigned peers = __match_any_sync(am, d);
+      const int leader = __ffs(peers) - 1;
+      int o = 0;
+      if (lane == leader) o = wh[warp][d], wh[warp][d] = o + __popc(peers);
+      o = __shfl_sync(peers, o, leader);
+      const int pos = o + __popc(peers & lt);
+      okeys[pos] = k;
+      ovals[pos] = first ? i : vals[i];
+    }
+    __syncwarp();
+  }
+}
+// segment of every cell in the sorted order: seg_off[c] = first position, cnt[c] = number of points; counts[4] = points binned
+__global__ void k_seg_bounds(const BuildJob *__restrict__ jobs, int final_parity) {
+  const BuildJob &j = jobs[blockIdx.y];
+  if (j.pt_cell == nullptr) return;
+  const int n = j.npts;
+  const int *keys = final_parity ? j.key2 : j.pt_cell;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int k = keys[i];
+    const int kp = i > 0 ? keys[i - 1] : -2, kn = i + 1 < n ? keys[i + 1] : -2;
+    if (k < 0) {
+      if (kp >= 0 || i == 0) j.counts[4] = i;  // the dropped points follow the binned ones
+      continue;
+    }
+    if (k != kp) j.seg_off[k] = i;
+    if (k != kn) {
+      j.cursor[k] = i + 1;  // segment end (cursor is free until k_cells builds its eigen list: consumed by k_seg_counts)
+      if (i == n - 1) j.counts[4] = n;
+    }
+  }
+}
+__global__ void k_seg_counts(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  if (j.pt_cell == nullptr) return;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < j.n_all; c += gridDim.x * blockDim.x) {
+    const int e = j.cursor[c];
+    j.cnt[c] = e > 0 ? e - j.seg_off[c] : 0;
+    j.cursor[c] = 0;
+  }
+}
+// voxel key (block * 64 + bit) of every cell, cells of a block in bit order
+__global__ void k_cell_keys(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  const int ntb = j.counts[1];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntb; t += gridDim.x * blockDim.x) {
+    const int b = j.tb_list[t];
+    unsigned long long m = j.amask[b];
+    int c = j.abase[b];
+    for (; m; m &= m - 1ull, c++) j.cell_key[c] = b * 64 + (__ffsll((long long)m) - 1);
   }
 }
 
@@ -677,7 +816,7 @@ __global__ void __launch_bounds__(128) k_cell_trace(const BuildJob *__restrict__
     }
     {
       const int nv = j.v_cnt[c];
-      const int *__restrict__ vids = j.v_seg2 + j.v_seg_off[c];
+      const int *__restrict__ vids = j.v_seg2 + j.v_seg_off[c];  // (host: v_seg2 = the visit sort's final buffer)
       double icov[9];
       bool icov_ok = false, icov_done = false;
       for (int q = 0; q < nv; q++) {
@@ -739,7 +878,7 @@ __global__ void __launch_bounds__(128, NDTB_KCELLS_MINBLOCKS) k_cells(const Buil
       if (occ <= 0.f) has = 0, emptied = true;
     }
     if (n > 0 && !emptied) {
-      const int *__restrict__ ids = j.seg2 + j.seg_off[c];
+      const int *__restrict__ ids = j.sorted_ids + j.seg_off[c];
       if (has || n >= 3) {
         // the additions stay in id order; the gathers of four points are issued together
         double ms0 = 0, ms1 = 0, ms2 = 0;
@@ -1079,6 +1218,7 @@ int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int ma
   k_extent<<<dim3(chunks_for(max_pts, 1024), n_which), 256, 0, s>>>(d_jobs, d_which, d_out);
   return 3;
 }
+static int launch_group_by_cell(const BuildJob *d_jobs, int n, int max_items, int max_cells, cudaStream_t s);
 int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, cudaStream_t s) {
   k_mark<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
   if (trace) {
@@ -1093,26 +1233,42 @@ int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, cudaStre
 int launch_trace_lists(const BuildJob *d_jobs, const BuildJob *d_vjobs, int n, int max_pts, int max_vis, int max_ntb, int max_cells,
                        cudaStream_t s) {
   k_trace_fill<<<dim3(chunks_for(max_pts, 128), n), 128, 0, s>>>(d_jobs);
-  k_count<<<dim3(chunks_for(max_vis, 1024), n), 256, 0, s>>>(d_vjobs);
-  k_segscan<<<n, 1024, 0, s>>>(d_vjobs);
-  k_scatter<<<dim3(chunks_for(max_vis, 1024), n), 256, 0, s>>>(d_vjobs);
-  k_sort_segments<<<dim3(chunks_for(max_ntb, 8), n), 256, 0, s>>>(d_vjobs);
+  const int ns = launch_group_by_cell(d_vjobs, n, max_vis, max_cells, s);
+  k_cell_keys<<<dim3(chunks_for(max_ntb, 128), n), 128, 0, s>>>(d_jobs);
   k_cell_trace<<<dim3(chunks_for(max_cells, 128), n), 128, 0, s>>>(d_jobs);
-  return 6;
+  return ns + 3;
 }
 int launch_transform_points(const float4 *d_in, float4 *d_out, int n, const float *d_T12, cudaStream_t s) {
   k_transform_points<<<chunks_for(n, 1024), 256, 0, s>>>(d_in, d_out, n, d_T12);
   return 1;
 }
+int sort_tile_points() { return RS_TILE; }
+int sort_passes(int max_cells) {
+  int bits = 1;
+  while ((1ll << bits) <= (long long)max_cells) bits++;
+  return (bits + 7) / 8;
+}
+// key -> cell id, stable radix sort of the ids by cell id, per-cell segments.  Returns the number of launches.
+static int launch_group_by_cell(const BuildJob *d_jobs, int n, int max_items, int max_cells, cudaStream_t s) {
+  const int tiles = (max_items + RS_TILE - 1) / RS_TILE > 0 ? (max_items + RS_TILE - 1) / RS_TILE : 1;
+  const int P = sort_passes(max_cells);
+  k_count<<<dim3(chunks_for(max_items, 1024), n), 256, 0, s>>>(d_jobs);
+  for (int p = 0; p < P; p++) {
+    k_rs_hist<<<dim3(tiles, n), RS_THREADS, 0, s>>>(d_jobs, 8 * p, p & 1);
+    k_rs_scan<<<n, 1024, 0, s>>>(d_jobs);
+    k_rs_scatter<<<dim3(tiles, n), RS_THREADS, 0, s>>>(d_jobs, 8 * p, p & 1, p == 0);
+  }
+  k_seg_bounds<<<dim3(chunks_for(max_items, 1024), n), 256, 0, s>>>(d_jobs, P & 1);
+  k_seg_counts<<<dim3(chunks_for(max_cells, 256), n), 256, 0, s>>>(d_jobs);
+  return 3 + 3 * P;
+}
 int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int max_cells, cudaStream_t s) {
-  k_count<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
-  k_segscan<<<n, 1024, 0, s>>>(d_jobs);
-  k_scatter<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
-  k_sort_segments<<<dim3(chunks_for(max_ntb, 8), n), 256, 0, s>>>(d_jobs);
+  const int ns = launch_group_by_cell(d_jobs, n, max_pts, max_cells, s);
+  k_cell_keys<<<dim3(chunks_for(max_ntb, 128), n), 128, 0, s>>>(d_jobs);
   k_cells<<<dim3(chunks_for(max_cells, 128), n), 128, 0, s>>>(d_jobs);
   k_eigen<<<dim3(chunks_for(max_cells, 128), n), 128, 0, s>>>(d_jobs);
   k_eigen_hard<<<dim3(chunks_for(max_cells / 16 + 1, 128), n), 128, 0, s>>>(d_jobs);
-  return 7;
+  return ns + 4;
 }
 int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s) {
   k_gscan<<<n, 1024, 0, s>>>(d_jobs);

@@ -29,8 +29,11 @@ struct BuildJob {
   int *counts;   // [8]: 0 n_all, 1 n touched blocks, 2 n gaussian cells, 3 n gaussian blocks, 4 points binned
   // per-point temporaries
   int *pt_cell;  // [npts] voxel key (block*64+bit) then cell id; -1 = dropped
-  int *seg_idx;  // [npts] point ids grouped by cell (arbitrary order inside a cell)
-  int *seg2;     // [npts] the same, ascending inside each cell
+  int *seg_idx;  // [npts] radix-sort ping-pong buffer (point ids)
+  int *seg2;     // [npts] point ids grouped by cell, ascending inside each cell (= insertion order of NDTCell::points_)
+  const int *sorted_ids;  // seg2 or seg_idx: where the last sort pass left the ids (depends on the number of passes)
+  int *key2;     // [npts] radix-sort ping-pong buffer (cell ids)
+  int *rs_hist;  // [256 * tiles] digit histograms of the sort tiles, digit-major
   // per-cell (valid after the popcount scan)
   int n_all;
   int *cnt, *seg_off, *cursor;
@@ -79,6 +82,8 @@ int launch_trace_lists(const BuildJob *d_jobs, const BuildJob *d_vjobs, int n, i
                        cudaStream_t s);
 int launch_transform_points(const float4 *d_in, float4 *d_out, int n, const float *d_T12, cudaStream_t s);
 int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int max_cells, cudaStream_t s);
+int sort_passes(int max_cells);  // 8-bit radix passes needed for cell ids 0..max_cells
+int sort_tile_points();  // points per radix-sort tile (sizing of BuildJob::rs_hist: 256 ints per tile)
 int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s);
 int launch_blockscan(const BuildJob *d_jobs, int n, cudaStream_t s);
 int launch_export(const BuildJob *d_job, int ntb, ndtb_cell *d_out, cudaStream_t s);

@@ -151,6 +151,10 @@ struct ndtb_map {
   bool grid_ready = false;
   GridDesc g;
   int nblk = 0;
+  // storage box of the dense block arrays (map_build.cuh BuildJob::boff / nbs); the whole grid unless allow_box
+  int boff[3] = {0, 0, 0}, nbs[3] = {0, 0, 0};
+  bool allow_box = false;  // temporaries of ndtb_register_scans: store only the box the points can occupy
+  double ext_maxdist = 0, ext_dz_min = 0, ext_dz_max = 0;  // extents found by the guess-size pass (about the centroid)
   // pending points (loadPointCloud / addPointCloud before computeNDTCells)
   struct Chunk {
     SlabP buf;
@@ -188,17 +192,32 @@ struct ndtb_map {
       g.cell[i] = cell[i];
       g.size[i] = (int32_t)std::abs(std::ceil(sm[i] / cell[i]));  // LazyGrid::setSize
       g.nb[i] = (g.size[i] + 3) / 4;
+      boff[i] = 0, nbs[i] = g.nb[i];
     }
     grid_ready = true;
     drop_cells();
   }
+  void fill_box(BuildJob &j) const {
+    for (int i = 0; i < 3; i++) j.boff[i] = boff[i], j.nbs[i] = nbs[i];
+  }
+  // guess-size grid: the points lie within maxDist of the centre (z: within the recorded extent) -> store that box only
+  void shrink_box() {
+    const double lo[3] = {-ext_maxdist, -ext_maxdist, -ext_dz_max}, hi[3] = {ext_maxdist, ext_maxdist, -ext_dz_min};
+    for (int i = 0; i < 3; i++) {
+      const double a = std::floor(lo[i] / g.cell[i] + 0.5) + g.size[i] / 2.0, b = std::floor(hi[i] / g.cell[i] + 0.5) + g.size[i] / 2.0;
+      int b0 = ((int)a >> 2) - 1, b1 = ((int)b >> 2) + 1;
+      b0 = std::max(b0, 0), b1 = std::min(b1, g.nb[i] - 1);
+      if (b1 < b0) b0 = 0, b1 = g.nb[i] - 1;
+      boff[i] = b0, nbs[i] = b1 - b0 + 1;
+    }
+  }
+  int64_t nblocks() const { return (int64_t)nbs[0] * nbs[1] * nbs[2]; }
   void drop_cells() {
     s_blocks.reset(), s_cells.reset();
     amask = nullptr, abase = nullptr, tb_list = nullptr, counts = nullptr;
     cmean = ccov = nullptr, cn = chas = nullptr, cocc = nullptr, gcell = nullptr, g2c = nullptr, table = nullptr;
     n_all = ntb = tsize = ng = ngb = 0;
   }
-  int64_t nblocks() const { return (int64_t)g.nb[0] * g.nb[1] * g.nb[2]; }
 };
 
 namespace {
@@ -279,6 +298,8 @@ int define_grids(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::
         m->set_grid(o[0], o[1], o[2], m->map_sizex, m->map_sizey, m->map_sizez);
       else
         m->set_grid(o[0], o[1], o[2], 4 * maxDist, 4 * maxDist, 3 * (maxz - minz));
+      m->ext_maxdist = maxDist, m->ext_dz_min = minz, m->ext_dz_max = maxz;
+      if (m->allow_box) m->shrink_box();
       m->is_first_load = false;
     }
   }
@@ -416,6 +437,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
     ndtb_map *m = maps[i];
     BuildJob &j = jobs[i];
     j.g = m->g;
+    m->fill_box(j);
     j.nblk = m->nblk;
     j.amask = (unsigned long long *)(s_b->p + ob[i].amask);
     j.abase = (int *)(s_b->p + ob[i].abase);
@@ -1136,6 +1158,7 @@ int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells,
     m->cell[i] = g->cell[i];
     m->g.cell[i] = g->cell[i], m->g.center[i] = g->center[i], m->g.size[i] = g->size[i], m->g.nb[i] = (g->size[i] + 3) / 4;
   }
+  for (int i = 0; i < 3; i++) m->boff[i] = 0, m->nbs[i] = m->g.nb[i];
   m->guess_size = false, m->is_first_load = false, m->grid_ready = true;
   m->drop_cells();
   m->pending.clear();
@@ -1155,6 +1178,7 @@ int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells,
   BuildJob j;
   std::memset(&j, 0, sizeof j);
   j.g = m->g, j.nblk = m->nblk;
+  m->fill_box(j);
   j.amask = (unsigned long long *)(s_b->p + o_amask), j.abase = (int *)(s_b->p + o_abase);
   j.tb_list = (int *)(s_b->p + o_tbl), j.counts = (int *)(s_b->p + o_counts);
   BuildJob *d_job = (BuildJob *)(s_t->p + o_job);
@@ -1219,6 +1243,7 @@ int64_t ndtb_map_export_cells(const ndtb_map *m, ndtb_cell *out, int64_t cap, in
   BuildJob j;
   std::memset(&j, 0, sizeof j);
   j.g = m->g, j.amask = m->amask, j.abase = m->abase, j.tb_list = m->tb_list, j.counts = m->counts;
+  m->fill_box(j);
   j.cmean = m->cmean, j.ccov = m->ccov, j.cn = m->cn, j.chas = m->chas, j.cocc = m->cocc;
   BuildJob *d_job = (BuildJob *)(tmp->p + ((sizeof(ndtb_cell) * (size_t)m->n_all + 255) & ~(size_t)255));
   CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
@@ -1500,6 +1525,7 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
     m->ctx = ctx;
     m->cell[0] = m->cell[1] = m->cell[2] = cell;
     std::memset(&m->g, 0, sizeof m->g);
+    m->allow_box = true;  // never merged into, exported or scored: only the Gaussian view outlives the build
     if (map_size && map_size[0] > 0 && map_size[1] > 0 && map_size[2] > 0)
       m->map_sizex = (float)map_size[0], m->map_sizey = (float)map_size[1], m->map_sizez = (float)map_size[2];
     maps[i] = m;
@@ -1568,6 +1594,7 @@ int ndtb_overlap_score_batch(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *re
       if (!map_ok(mm[i])) return NDTB_ERR_GRID;
       BuildJob &b = j[(size_t)(2 * l + i)];
       b.g = mm[i]->g;
+      mm[i]->fill_box(b);
       if (mm[i]->n_all > 0)
         b.amask = mm[i]->amask, b.abase = mm[i]->abase, b.tb_list = mm[i]->tb_list, b.counts = mm[i]->counts, b.cocc = mm[i]->cocc;
     }

@@ -10,10 +10,13 @@
 //       call sites ndt_feature_fuser_hmt.cpp:94,227,486
 //
 // Pipeline (all order-independent pieces are parallel; the order-dependent sums are done in point-index order):
-//   centroid/extent (guess-size grids only) -> mark touched voxels in a 1-bit-per-voxel block mask ->
-//   popcount scan (cell numbering = (block, bit) order, touched-block list) -> per-cell counts -> segment scan ->
-//   scatter point ids -> per cell: rank-sort ids, sequential mean, sequential scatter matrix, merge with the
-//   previous (N, mean, cov), occupancy, 3x3 Jacobi eigen clamp -> Gaussian view (compact cells + block hash table).
+//   centroid/extent (guess-size grids only) -> mark touched voxels in a 1-bit-per-voxel block mask (dense over the
+//   storage box) [-> trace the rays of addPointCloud: mark + list the cells every ray meets] ->
+//   popcount scan (cell numbering = (block, bit) order, touched-block list) -> cell id per point -> stable LSD radix
+//   sort of the point ids by cell id (ids stay ascending inside a cell = insertion order of NDTCell::points_) ->
+//   per-cell segments [-> per cell: free-space evidence of the rays in tracing order] -> per cell: sequential mean,
+//   sequential scatter matrix, merge with the previous (N, mean, cov), occupancy, 3x3 Jacobi eigen clamp ->
+//   Gaussian view (compact cells + block hash table).
 #include "map_build.cuh"
 
 namespace ndtb {
@@ -204,6 +207,17 @@ __global__ void k_extent(const BuildJob *__restrict__ jobs, const int *__restric
 
 __device__ __forceinline__ int cta_excl_scan(int v, int *tot, int *wsum);
 
+// storage block id of a voxel inside the job's storage box, -1 outside
+__device__ __forceinline__ int sblock_id(const BuildJob &j, int ix, int iy, int iz) {
+  const int bx = (ix >> 2) - j.boff[0], by = (iy >> 2) - j.boff[1], bz = (iz >> 2) - j.boff[2];
+  if (bx < 0 || by < 0 || bz < 0 || bx >= j.nbs[0] || by >= j.nbs[1] || bz >= j.nbs[2]) return -1;
+  return (bx * j.nbs[1] + by) * j.nbs[2] + bz;
+}
+// block coordinates in the full grid of a storage block id
+__device__ __forceinline__ void sblock_coords(const BuildJob &j, int b, int &bx, int &by, int &bz) {
+  bz = b % j.nbs[2] + j.boff[2], by = (b / j.nbs[2]) % j.nbs[1] + j.boff[1], bx = b / (j.nbs[2] * j.nbs[1]) + j.boff[0];
+}
+
 // ---- free-space ray trace (NDTMap::addPointCloud + LazyGrid::traceLine [upstream]) ---------------------------
 // call sites ndt_feature_fuser_hmt.cpp:92 (initialize) and :485 (update).  A pending point that belongs to a trace
 // segment is a ray from the segment's origin: the ray is dropped (end point included) when it is longer than 200 m or
@@ -242,7 +256,8 @@ __device__ __forceinline__ void ray_walk(const BuildJob &j, const TraceSeg &sg, 
     if (x == xo && y == yo && z == zo) continue;
     xo = x, yo = y, zo = z;
     if (!in_grid(j.g, x, y, z)) continue;
-    visit(block_id(j.g, x, y, z) * 64 + block_bit(x, y, z));
+    const int sb = sblock_id(j, x, y, z);
+    if (sb >= 0) visit(sb * 64 + block_bit(x, y, z));
   }
 }
 
@@ -334,8 +349,9 @@ __global__ void k_mark(const BuildJob *__restrict__ jobs) {
         }
       }
       if (live && voxel_index(j.g, (double)p[u].x, (double)p[u].y, (double)p[u].z, ix, iy, iz) && in_grid(j.g, ix, iy, iz)) {
-        b[u] = block_id(j.g, ix, iy, iz), bit[u] = block_bit(ix, iy, iz);
-        key[u] = b[u] * 64 + bit[u];
+        b[u] = sblock_id(j, ix, iy, iz), bit[u] = block_bit(ix, iy, iz);
+        key[u] = b[u] >= 0 ? b[u] * 64 + bit[u] : -1;  // (outside the storage box: cannot happen, the box bounds the points)
+        b[u] = b[u] >= 0 ? b[u] : 0;
       }
     }
     // ~90 % of the points fall into a voxel that is already marked: look before taking the (contended) atomic.  A stale
@@ -564,30 +580,6 @@ __global__ void k_cell_keys(const BuildJob *__restrict__ jobs) {
   }
 }
 
-__global__ void __launch_bounds__(1024) k_segscan(const BuildJob *__restrict__ jobs) {
-  const BuildJob &j = jobs[blockIdx.x];
-  __shared__ int wsum[32];
-  int run = 0;
-  for (int base = 0; base < j.n_all; base += 1024) {
-    const int c = base + threadIdx.x;
-    const int v = c < j.n_all ? j.cnt[c] : 0;
-    int t;
-    const int e = cta_excl_scan(v, &t, wsum);
-    if (c < j.n_all) j.seg_off[c] = run + e;
-    run += t;
-  }
-  if (threadIdx.x == 0) j.counts[4] = run;  // points binned
-}
-
-__global__ void k_scatter(const BuildJob *__restrict__ jobs) {
-  const BuildJob &j = jobs[blockIdx.y];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
-    const int c = j.pt_cell[i];
-    if (c < 0) continue;
-    j.seg_idx[j.seg_off[c] + j.seg2[i]] = i;  // the rank k_count drew: no second round of atomics
-  }
-}
-
 // ---- per-cell Gaussians --------------------------------------------------------------------------------
 // NDTCell::rescaleCovariance [upstream]: any eigenvalue <= 0 -> no Gaussian; clamp to >= max/1000 (fixture-pinned)
 // max_sweeps < 64: *deferred is set (and cov left untouched) when the Jacobi iteration needs more sweeps than that
@@ -610,125 +602,6 @@ __device__ bool rescale_covariance(double *cov, int max_sweeps = 64, bool *defer
         cov[i * 3 + k] = s;
       }
   return true;
-}
-
-// (a) one warp per touched block: record every cell's voxel key and sort its point ids ascending
-// (= insertion order of NDTCell::points_): shuffle ranking for n <= 32, a 64-element bitonic network in shared
-// memory up to 64, a stable warp radix sort beyond (cells next to the sensor hold thousands of points).
-constexpr int SORT_BITONIC_MAX = 64;
-
-// stable LSD radix sort (8-bit digits) of n point ids by one warp; ping-pongs between a and b, result in b
-__device__ void warp_radix_sort(int *a, int *b, int n, int bits, int *hist /*256, shared*/, int lane) {
-  const unsigned lt = (1u << lane) - 1u;
-  const int passes = (bits + 7) / 8;
-  int *in = a, *out = b;
-  if ((passes & 1) == 0) {  // even number of passes: start from b so that the last pass lands in b
-    for (int e = lane; e < n; e += 32) b[e] = a[e];
-    __syncwarp();
-    in = b, out = a;
-  }
-  for (int p = 0, shift = 0; p < passes; p++, shift += 8) {
-    for (int i = lane; i < 256; i += 32) hist[i] = 0;
-    __syncwarp();
-    for (int e = lane; e < n; e += 32) atomicAdd(&hist[(in[e] >> shift) & 255], 1);
-    __syncwarp();
-    int local[8], sum = 0;
-#pragma unroll
-    for (int q = 0; q < 8; q++) local[q] = hist[lane * 8 + q], sum += local[q];
-    int incl = sum;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int t = __shfl_up_sync(FULL, incl, off);
-      if (lane >= off) incl += t;
-    }
-    int run = incl - sum;
-#pragma unroll
-    for (int q = 0; q < 8; q++) hist[lane * 8 + q] = run, run += local[q];
-    __syncwarp();
-    for (int base = 0; base < n; base += 32) {  // chunks in order: stable
-      const int e = base + lane;
-      const bool act = e < n;
-      const int v = act ? in[e] : 0;
-      const int d = (v >> shift) & 255;
-      const unsigned am = __ballot_sync(FULL, act);
-      if (act) {
-        const unsigned peers = __match_any_sync(am, d);
-        const int leader = __ffs(peers) - 1;
-        int off = 0;
-        if (lane == leader) off = hist[d], hist[d] = off + __popc(peers);
-        off = __shfl_sync(peers, off, leader);
-        out[off + __popc(peers & lt)] = v;
-      }
-      __syncwarp();
-    }
-    int *t = in;
-    in = out, out = t;
-  }
-}
-
-__device__ __forceinline__ int nth_set_bit(unsigned long long m, int k) {  // position of the k-th (0-based) set bit
-  const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
-  const int pl = __popc(lo);
-  return k < pl ? (int)__fns(lo, 0, k + 1) : 32 + (int)__fns(hi, 0, k - pl + 1);
-}
-
-// The metadata of up to 32 cells of a block (count, segment offset, voxel key) is fetched by the lanes in parallel and
-// the ids of the next small cell are loaded while the current one is being ranked: one dependent round trip per cell
-// instead of three.
-__global__ void __launch_bounds__(256) k_sort_segments(const BuildJob *__restrict__ jobs) {
-  __shared__ int sbuf[8][256];
-  const BuildJob &j = jobs[blockIdx.y];
-  const int lane = threadIdx.x & 31;
-  int *sb = sbuf[threadIdx.x >> 5];
-  const int ntb = j.cnt ? j.counts[1] : 0;  // a map without visit lists in a ray-traced batch has no per-visit arrays
-  const int bits = 32 - __clz(j.npts > 1 ? j.npts - 1 : 1);
-  for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ntb; t += gridDim.x * 8) {
-    const int b = j.tb_list[t];
-    const unsigned long long m = j.amask[b];
-    const int c0 = j.abase[b], nc = __popcll(m);
-    for (int base = 0; base < nc; base += 32) {
-      const int ci = base + lane;
-      int my_n = 0, my_off = 0;
-      if (ci < nc) {
-        my_n = j.cnt[c0 + ci], my_off = j.seg_off[c0 + ci];
-        j.cell_key[c0 + ci] = b * 64 + nth_set_bit(m, ci);
-      }
-      const int nround = min(32, nc - base);
-      int n = __shfl_sync(FULL, my_n, 0), off = __shfl_sync(FULL, my_off, 0);
-      int v = (lane < n && n <= 32) ? j.seg_idx[off + lane] : 0x7fffffff;
-      for (int q = 0; q < nround; q++) {
-        int n2 = 0, off2 = 0, v2 = 0x7fffffff;
-        if (q + 1 < nround) {
-          n2 = __shfl_sync(FULL, my_n, q + 1), off2 = __shfl_sync(FULL, my_off, q + 1);
-          if (lane < n2 && n2 <= 32) v2 = j.seg_idx[off2 + lane];
-        }
-        if (n > 0) {
-          int *seg = j.seg_idx + off;
-          int *srt = j.seg2 + off;
-          if (n <= 32) {  // ranks by n broadcasts
-            int r = 0;
-            for (int e = 0; e < n; e++) r += __shfl_sync(FULL, v, e) < v;
-            if (lane < n) srt[r] = v;
-          } else if (n <= SORT_BITONIC_MAX) {  // 64-element bitonic network in shared memory
-            for (int e = lane; e < 64; e += 32) sb[e] = e < n ? seg[e] : 0x7fffffff;
-            __syncwarp();
-            for (int k = 2; k <= 64; k <<= 1)
-              for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                const int i0 = 2 * lane - (lane & (jj - 1)), i1 = i0 + jj;
-                const int a0 = sb[i0], a1 = sb[i1];
-                if ((a0 > a1) == ((i0 & k) == 0)) sb[i0] = a1, sb[i1] = a0;
-                __syncwarp();
-              }
-            for (int e = lane; e < n; e += 32) srt[e] = sb[e];
-            __syncwarp();
-          } else {  // any size: stable radix sort through global memory (L1/L2 resident segments)
-            warp_radix_sort(seg, srt, n, bits, sb, lane);
-          }
-        }
-        n = n2, off = off2, v = v2;
-      }
-    }
-  }
 }
 
 // Occupancy evidence of one traced ray for a cell that holds a Gaussian (NDTMap::addPointCloud [upstream], REFACTORED
@@ -1018,9 +891,12 @@ __global__ void k_gfill(const BuildJob *__restrict__ jobs) {
     const unsigned long long gm = j.gmask_t[t];
     if (!gm) continue;
     const int b = j.tb_list[t];
-    unsigned h = hash_block(b, j.tsize);
+    int gx, gy, gz;
+    sblock_coords(j, b, gx, gy, gz);
+    const int gkey = (gx * j.g.nb[1] + gy) * j.g.nb[2] + gz;  // the matcher probes with block ids of the full grid
+    unsigned h = hash_block(gkey, j.tsize);
     for (;;) {
-      const int prev = atomicCAS(&j.table[h].key, -1, b);
+      const int prev = atomicCAS(&j.table[h].key, -1, gkey);
       if (prev == -1) break;
       h = (h + 1) & (unsigned)(j.tsize - 1);
     }
@@ -1047,7 +923,8 @@ __global__ void k_export(const BuildJob *__restrict__ jobs, ndtb_cell *__restric
   const int ntb = j.counts[1];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntb; t += gridDim.x * blockDim.x) {
     const int b = j.tb_list[t];
-    const int bz = b % j.g.nb[2], by = (b / j.g.nb[2]) % j.g.nb[1], bx = b / (j.g.nb[2] * j.g.nb[1]);
+    int bx, by, bz;
+    sblock_coords(j, b, bx, by, bz);
     unsigned long long m = j.amask[b];
     int c = j.abase[b];
     for (; m; m &= m - 1ull, c++) {
@@ -1081,7 +958,12 @@ __global__ void k_cells_voxel(const BuildJob *__restrict__ jobs, const ndtb_cell
       atomicExch(err, 1);
       continue;
     }
-    const int b = block_id(j.g, ix, iy, iz), bit = block_bit(ix, iy, iz);
+    const int b = sblock_id(j, ix, iy, iz), bit = block_bit(ix, iy, iz);
+    if (b < 0) {
+      vox[i] = -1;
+      atomicExch(err, 1);
+      continue;
+    }
     vox[i] = b * 64 + bit;
     atomicOr(j.amask + b, 1ull << bit);
   }
@@ -1148,7 +1030,8 @@ __global__ void __launch_bounds__(256) k_overlap(const BuildJob *__restrict__ jo
   const int ntb = mov.counts[1];
   for (int t = threadIdx.x; t < ntb; t += blockDim.x) {
     const int b = mov.tb_list[t];
-    const int bz = b % mov.g.nb[2], by = (b / mov.g.nb[2]) % mov.g.nb[1], bx = b / (mov.g.nb[2] * mov.g.nb[1]);
+    int bx, by, bz;
+    sblock_coords(mov, b, bx, by, bz);
     unsigned long long m = mov.amask[b];
     int c = mov.abase[b];
     for (; m; m &= m - 1ull, c++) {
@@ -1165,7 +1048,8 @@ __global__ void __launch_bounds__(256) k_overlap(const BuildJob *__restrict__ jo
       for (int a = 0; a < 3; a++) pt[a] = (float)((T.R[a * 3] * e[0] + T.R[a * 3 + 1] * e[1] + T.R[a * 3 + 2] * e[2]) + T.t[a]);
       int ix, iy, iz;
       if (!voxel_index(ref.g, (double)pt[0], (double)pt[1], (double)pt[2], ix, iy, iz) || !in_grid(ref.g, ix, iy, iz)) continue;
-      const int rb = block_id(ref.g, ix, iy, iz), rbit = block_bit(ix, iy, iz);
+      const int rb = sblock_id(ref, ix, iy, iz), rbit = block_bit(ix, iy, iz);
+      if (rb < 0) continue;
       const unsigned long long rm = ref.amask[rb];
       if (!(rm >> rbit & 1ull)) continue;
       const double ro = occ_rescaled(ref.cocc[ref.abase[rb] + __popcll(rm & ((1ull << rbit) - 1ull))]);
@@ -1203,6 +1087,9 @@ __global__ void k_transform_points(const float4 *__restrict__ in, float4 *__rest
 }
 
 // ---- launch wrappers (host) ---------------------------------------------------------------------------
+#ifndef NDTB_PTS_PER_CTA
+#define NDTB_PTS_PER_CTA 16384  // points per CTA of the streaming per-point kernels (grid-stride loops; B200 A/B per 1184 maps: 1024 -> 14.3 ms, 4096 -> 13.0 ms, 16384 -> 12.6 ms)
+#endif
 static inline int chunks_for(int n, int per) {
   int c = (n + per - 1) / per;
   return c < 1 ? 1 : (c > 1024 ? 1024 : c);
@@ -1215,12 +1102,12 @@ int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int ma
   const int max_chunks = (max_pts + CEN_CHUNK - 1) / CEN_CHUNK;
   k_centroid_chunks<<<dim3(chunks_for(max_chunks, 4), n_which), 128, 0, s>>>(d_jobs, d_which, d_rec_off, d_recs);
   k_centroid<<<n_which, 32, 0, s>>>(d_jobs, d_which, d_rec_off, d_recs, d_out);
-  k_extent<<<dim3(chunks_for(max_pts, 1024), n_which), 256, 0, s>>>(d_jobs, d_which, d_out);
+  k_extent<<<dim3(chunks_for(max_pts, NDTB_PTS_PER_CTA), n_which), 256, 0, s>>>(d_jobs, d_which, d_out);
   return 3;
 }
 static int launch_group_by_cell(const BuildJob *d_jobs, int n, int max_items, int max_cells, cudaStream_t s);
 int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, cudaStream_t s) {
-  k_mark<<<dim3(chunks_for(max_pts, 1024), n), 256, 0, s>>>(d_jobs);
+  k_mark<<<dim3(chunks_for(max_pts, NDTB_PTS_PER_CTA), n), 256, 0, s>>>(d_jobs);
   if (trace) {
     k_trace_count<<<dim3(chunks_for(max_pts, 128), n), 128, 0, s>>>(d_jobs);
     k_rayscan<<<n, 1024, 0, s>>>(d_jobs);
@@ -1252,13 +1139,13 @@ int sort_passes(int max_cells) {
 static int launch_group_by_cell(const BuildJob *d_jobs, int n, int max_items, int max_cells, cudaStream_t s) {
   const int tiles = (max_items + RS_TILE - 1) / RS_TILE > 0 ? (max_items + RS_TILE - 1) / RS_TILE : 1;
   const int P = sort_passes(max_cells);
-  k_count<<<dim3(chunks_for(max_items, 1024), n), 256, 0, s>>>(d_jobs);
+  k_count<<<dim3(chunks_for(max_items, NDTB_PTS_PER_CTA), n), 256, 0, s>>>(d_jobs);
   for (int p = 0; p < P; p++) {
     k_rs_hist<<<dim3(tiles, n), RS_THREADS, 0, s>>>(d_jobs, 8 * p, p & 1);
     k_rs_scan<<<n, 1024, 0, s>>>(d_jobs);
     k_rs_scatter<<<dim3(tiles, n), RS_THREADS, 0, s>>>(d_jobs, 8 * p, p & 1, p == 0);
   }
-  k_seg_bounds<<<dim3(chunks_for(max_items, 1024), n), 256, 0, s>>>(d_jobs, P & 1);
+  k_seg_bounds<<<dim3(chunks_for(max_items, NDTB_PTS_PER_CTA), n), 256, 0, s>>>(d_jobs, P & 1);
   k_seg_counts<<<dim3(chunks_for(max_cells, 256), n), 256, 0, s>>>(d_jobs);
   return 3 + 3 * P;
 }

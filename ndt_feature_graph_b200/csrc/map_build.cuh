@@ -17,6 +17,12 @@ struct TraceSeg {
 // One map of a batched build.  Pointers address this map's slice of the batch slabs.
 struct BuildJob {
   GridDesc g;
+  // Storage box of the dense per-block arrays (amask / abase), in 4x4x4 blocks: boff = first stored block per axis, nbs =
+  // stored blocks per axis.  Normally the whole grid (boff = 0, nbs = g.nb).  A guess-size grid spans 4 x maxDist per axis
+  // although its points only occupy the central +-maxDist: the temporaries of ndtb_register_scans store that box only
+  // (1/12 of the blocks at C2: 12x less to clear and to scan).  Cell order ((bx, by, bz) lexicographic, then bit) and the
+  // block ids of the matcher's hash table are those of the full grid either way.
+  int boff[3], nbs[3];
   const float4 *pts;   // pending points (pcl::PointXYZ layout), device memory
   int npts;
   double range_limit;  // loadPointCloud range filter; <= 0: none

@@ -36,8 +36,8 @@ UNIT = "registrations/s"
 WORKLOAD = "C2: 3-D NDT-D2D scan-pair registration (map build x2 + match + covariance), 100k-pt synthetic Velodyne-like scans, 0.5 m voxels"
 CELL = 0.5
 # DRAM traffic of the match kernel per 592-pair step: constant from the committed ncu capture, not a live measurement
-NCU_TRAFFIC_GB_592 = 3.272
-NCU_TRAFFIC_SOURCE = "committed ncu --set full capture profiles/r02a_match_kernel_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum)"
+NCU_TRAFFIC_GB_592 = 3.133
+NCU_TRAFFIC_SOURCE = "committed ncu --set full capture profiles/r02b_match_kernel_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, main 3.0727 + 0.0404 GB, finishing launch 0.0202 GB)"
 # fp64 issue rate of a B200 SM: 64 DFMA / clk / SM (40 TFLOP/s at 148 SMs x 1.965 GHz x 2 flop)
 FP64_FMA_PER_CLK_SM = 64
 

@@ -56,6 +56,14 @@ struct ndtb_ctx {
   // second launch (stragglers, about half of the SMs) is still working
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+  // small host->device uploads (job descriptors, poses, single scans) bypass the copy engine: see h2d_small
+  static constexpr int STG_SEGS = 8;
+  static constexpr size_t STG_SEG_BYTES = (size_t)4 << 20, STG_MAX = (size_t)1 << 20;
+  char *stg_host = nullptr, *stg_dev = nullptr;
+  cudaEvent_t stg_ev[STG_SEGS] = {};
+  bool stg_used[STG_SEGS] = {};
+  int stg_seg = 0;
+  size_t stg_head = 0;
 };
 
 #define CU_TRY(ctx, expr)                                                                           \
@@ -84,6 +92,55 @@ struct DeviceGuard {
 };
 
 namespace {
+
+// ---- small uploads without the copy engine -----------------------------------------------------------------------
+// The H2D copy engine serves its queue in submission order ACROSS streams: a 470 KB job-descriptor upload issued while
+// 1.9 GB of scans are queued on the copy stream (this context's or another lane's) waits for all of them — measured on the
+// B200 box: the first chunk's build started 34 ms late, after the last scan had arrived.  Uploads of up to 1 MB therefore go
+// through a pinned, device-mapped staging ring and a copy kernel on the consuming stream, which depends on nothing but
+// that stream.  A ring segment is reused only after the event behind its last copy kernel has completed.
+__global__ void k_upload16(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_upload1(const unsigned char *__restrict__ src, unsigned char *__restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+cudaError_t h2d_small(ndtb_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  static const bool no_staging = std::getenv("NDTB_NO_STAGING") != nullptr;  // A/B switch for measurements
+  if (no_staging || bytes > ndtb_ctx::STG_MAX || st != ctx->stream) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  if (!ctx->stg_host) {
+    cudaError_t e = cudaHostAlloc((void **)&ctx->stg_host, ndtb_ctx::STG_SEGS * ndtb_ctx::STG_SEG_BYTES, cudaHostAllocMapped);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaHostGetDevicePointer((void **)&ctx->stg_dev, ctx->stg_host, 0)) != cudaSuccess) return e;
+    for (auto &ev : ctx->stg_ev)
+      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (ctx->stg_head + need > ndtb_ctx::STG_SEG_BYTES) {  // next segment: wait until its previous contents were consumed
+    ctx->stg_seg = (ctx->stg_seg + 1) % ndtb_ctx::STG_SEGS, ctx->stg_head = 0;
+    if (ctx->stg_used[ctx->stg_seg]) {
+      const cudaError_t e = cudaEventSynchronize(ctx->stg_ev[ctx->stg_seg]);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  const size_t at = (size_t)ctx->stg_seg * ndtb_ctx::STG_SEG_BYTES + ctx->stg_head;
+  ctx->stg_head += need;
+  std::memcpy(ctx->stg_host + at, src, bytes);
+  if ((((uintptr_t)dst | bytes) & 15) == 0) {
+    const size_t n = bytes / 16;
+    k_upload16<<<(unsigned)std::min<size_t>((n + 255) / 256, 296), 256, 0, st>>>((const uint4 *)(ctx->stg_dev + at), (uint4 *)dst, n);
+  } else {
+    k_upload1<<<(unsigned)std::min<size_t>((bytes + 255) / 256, 296), 256, 0, st>>>((const unsigned char *)(ctx->stg_dev + at),
+                                                                                  (unsigned char *)dst, bytes);
+  }
+  ctx->launches++;
+  ctx->stg_used[ctx->stg_seg] = true;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return cudaEventRecord(ctx->stg_ev[ctx->stg_seg], st);
+}
 
 // NDTB_PROFILE=1: host-side phase timer (synchronises the stream at every mark; debugging aid, never on in benchmarks)
 struct PhaseTimer {
@@ -267,9 +324,9 @@ int define_grids(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::
     SlabP s;
     if (int rc = slab_alloc(ctx, c.off, s)) return rc;
     std::vector<double> gs(8 * (size_t)W);
-    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_j, jobs.data(), sizeof(BuildJob) * W, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_w, ident.data(), 4 * (size_t)W, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_ro, rec_off.data(), 8 * (size_t)(W + 1), cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, h2d_small(ctx, s->p + o_j, jobs.data(), sizeof(BuildJob) * W, st));
+    CU_TRY(ctx, h2d_small(ctx, s->p + o_w, ident.data(), 4 * (size_t)W, st));
+    CU_TRY(ctx, h2d_small(ctx, s->p + o_ro, rec_off.data(), 8 * (size_t)(W + 1), st));
     CU_TRY(ctx, cudaMemsetAsync(s->p + o_gs, 0, 64 * (size_t)W, st));
     ctx->launches += launch_guess((const BuildJob *)(s->p + o_j), (const int *)(s->p + o_w), W, max_pts, (const long long *)(s->p + o_ro),
                                   (double *)(s->p + o_rec), (double *)(s->p + o_gs), st);
@@ -462,7 +519,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
     if (!empty[i]) live.push_back(jobs[i]), live_idx.push_back(i);
   const int L = (int)live.size();
   if (L == 0) return NDTB_OK;
-  CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, h2d_small(ctx, d_jobs, live.data(), sizeof(BuildJob) * L, st));
   ctx->launches += launch_mark(d_jobs, L, max_pts, any_trace, st);
   CU_TRY(ctx, cudaGetLastError());
   std::vector<int> cnts_all(8 * (size_t)M), cnts(8 * (size_t)L);
@@ -527,7 +584,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
       j.v_seg2 = (int *)(s_t2->p + (odd ? oc[l].vseg2 : oc[l].vidx));
     }
   }
-  CU_TRY(ctx, cudaMemcpyAsync(d_jobs, live.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, h2d_small(ctx, d_jobs, live.data(), sizeof(BuildJob) * L, st));
   pt.mark("alloc C");
   SlabP s_vjobs;
   if (any_trace) {  // per-cell visit lists through the points' counting sort: the same kernels on the per-visit arrays
@@ -543,7 +600,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
       if (!live[l].n_seg) v.n_all = 0, v.cnt = nullptr;  // nothing to do for a map without traced rays
     }
     if (int rc = slab_alloc(ctx, sizeof(BuildJob) * L, s_vjobs)) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(s_vjobs->p, vj.data(), sizeof(BuildJob) * L, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, h2d_small(ctx, s_vjobs->p, vj.data(), sizeof(BuildJob) * L, st));
     ctx->launches += launch_trace_lists(d_jobs, (const BuildJob *)s_vjobs->p, L, max_pts, max_vis, max_ntb, max_cells, st);
     CU_TRY(ctx, cudaGetLastError());
   }
@@ -576,8 +633,8 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
 int stage_points(ndtb_ctx *ctx, const float *pts, int64_t n, int mem, SlabP &out) {
   if (int rc = slab_alloc(ctx, 16 * (size_t)std::max<int64_t>(n, 1), out)) return rc;
   if (n > 0)
-    CU_TRY(ctx, cudaMemcpyAsync(out->p, pts, 16 * (size_t)n, mem == NDTB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                ctx->stream));
+    CU_TRY(ctx, mem == NDTB_MEM_DEVICE ? cudaMemcpyAsync(out->p, pts, 16 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream)
+                                       : h2d_small(ctx, out->p, pts, 16 * (size_t)n, ctx->stream));
   return NDTB_OK;
 }
 
@@ -666,9 +723,9 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
   ndtb_result *d_res = out_mem == NDTB_MEM_DEVICE ? res : (ndtb_result *)(s->p + o_res);
   const bool do_cov = with_cov && cov36s;
   double *d_cov = do_cov ? (out_mem == NDTB_MEM_DEVICE ? cov36s : (double *)(s->p + o_cov)) : nullptr;
-  CU_TRY(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(MatchJob) * n, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, h2d_small(ctx, d_jobs, jobs.data(), sizeof(MatchJob) * n, st));
   if (do_cov) {
-    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_goff, gt_off.data(), 8 * n, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, h2d_small(ctx, s->p + o_goff, gt_off.data(), 8 * n, st));
     CU_TRY(ctx, cudaMemsetAsync(s->p + o_gt, 0, 48 * gt_total, st));
   }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -807,6 +864,11 @@ void ndtb_ctx_destroy(ndtb_ctx *ctx) {
   if (!ctx) return;
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream), cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stg_host) {
+    for (cudaEvent_t e : ctx->stg_ev)
+      if (e) cudaEventDestroy(e);
+    cudaFreeHost(ctx->stg_host);
+  }
   for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream), cudaStreamDestroy(ctx->aux_stream);
   for (cudaEvent_t e : ctx->aux_ev)
@@ -1127,10 +1189,18 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
     }
     for (; cc <= n_chunks; cc++) cbeg[cc] = n_maps;
   }
+  static const bool prof_copies = std::getenv("NDTB_PROFILE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  if (prof_copies) {
+    tev.resize((size_t)n_chunks + 1);
+    for (auto &e : tev) cudaEventCreate(&e);
+    cudaEventRecord(tev[0], cs);
+  }
   for (int k = 0; k < n_chunks; k++) {
     for (int64_t i = cbeg[k]; i < cbeg[k + 1]; i++)
       if (n_pts[i] > 0) CU_TRY(ctx, cudaMemcpyAsync(big->p + off[i], pts[i], 16 * (size_t)n_pts[i], cudaMemcpyHostToDevice, cs));
     if (n_chunks > 1) CU_TRY(ctx, cudaEventRecord(ctx->copy_events[k], cs));
+    if (prof_copies) cudaEventRecord(tev[(size_t)k + 1], cs);
   }
   pt.mark("enqueue H2D");
   int rc = NDTB_OK;
@@ -1146,6 +1216,15 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
   }
   if (rc != NDTB_OK && n_chunks > 1) cudaStreamSynchronize(cs);  // the slab must outlive the copies in flight
   pt.mark("build_batch");
+  if (prof_copies) {
+    cudaStreamSynchronize(cs);
+    for (int k = 0; k < n_chunks; k++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tev[0], tev[(size_t)k + 1]);
+      std::fprintf(stderr, "[ndtb] H2D chunk %d done at %.3f ms (maps %lld..%lld)\n", k, ms, (long long)cbeg[k], (long long)cbeg[k + 1]);
+    }
+    for (auto &e : tev) cudaEventDestroy(e);
+  }
   return rc;
 }
 
@@ -1174,7 +1253,7 @@ int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells,
   if (int rc = slab_alloc(ctx, ct.off, s_t)) return rc;
   CU_TRY(ctx, cudaMemsetAsync(s_b->p, 0, s_b->bytes, st));
   CU_TRY(ctx, cudaMemsetAsync(s_t->p + o_err, 0, 4, st));
-  if (n > 0) CU_TRY(ctx, cudaMemcpyAsync(s_t->p + o_cells, cells, sizeof(ndtb_cell) * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (n > 0) CU_TRY(ctx, h2d_small(ctx, s_t->p + o_cells, cells, sizeof(ndtb_cell) * (size_t)n, st));
   BuildJob j;
   std::memset(&j, 0, sizeof j);
   j.g = m->g, j.nblk = m->nblk;
@@ -1184,7 +1263,7 @@ int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells,
   BuildJob *d_job = (BuildJob *)(s_t->p + o_job);
   const ndtb_cell *d_cells = (const ndtb_cell *)(s_t->p + o_cells);
   int *d_vox = (int *)(s_t->p + o_vox), *d_err = (int *)(s_t->p + o_err);
-  CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, h2d_small(ctx, d_job, &j, sizeof j, st));
   ctx->launches += launch_from_cells_voxel(d_job, d_cells, (int)n, use_idx, d_vox, d_err, st);
   ctx->launches += launch_blockscan(d_job, 1, st);
   int cnts[8], err = 0;
@@ -1208,7 +1287,7 @@ int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells,
   j.g2c = (int *)(s_c->p + o_g2c), j.table = (HashEntry *)(s_c->p + o_table);
   j.gmask_t = (unsigned long long *)(s_c->p + o_gm), j.gbase_t = (int *)(s_c->p + o_gb);
   CU_TRY(ctx, cudaMemsetAsync(j.table, 0xFF, sizeof(HashEntry) * (size_t)tsize, st));
-  CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, h2d_small(ctx, d_job, &j, sizeof j, st));
   ctx->launches += launch_from_cells_place(d_job, d_cells, (int)n, d_vox, st);
   ctx->launches += launch_gview(d_job, 1, std::max(ntb, 1), st);
   CU_TRY(ctx, cudaMemcpyAsync(cnts, j.counts, 32, cudaMemcpyDeviceToHost, st));
@@ -1246,7 +1325,7 @@ int64_t ndtb_map_export_cells(const ndtb_map *m, ndtb_cell *out, int64_t cap, in
   m->fill_box(j);
   j.cmean = m->cmean, j.ccov = m->ccov, j.cn = m->cn, j.chas = m->chas, j.cocc = m->cocc;
   BuildJob *d_job = (BuildJob *)(tmp->p + ((sizeof(ndtb_cell) * (size_t)m->n_all + 255) & ~(size_t)255));
-  CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, h2d_small(ctx, d_job, &j, sizeof j, ctx->stream));
   ctx->launches += launch_export(d_job, m->ntb, (ndtb_cell *)tmp->p, ctx->stream);
   std::vector<ndtb_cell> h((size_t)m->n_all);
   CU_TRY(ctx, cudaMemcpyAsync(h.data(), tmp->p, sizeof(ndtb_cell) * (size_t)m->n_all, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1270,16 +1349,19 @@ int64_t ndtb_map_point_indices(const ndtb_map *m, const float *pts, int64_t n, i
   ndtb_ctx *ctx = m->ctx;
   if (n == 0) return 0;
   SlabP pbuf, obuf;
+  PhaseTimer pt(ctx, "point_indices");
   const float4 *d_pts = (const float4 *)pts;
   if (mem != NDTB_MEM_DEVICE) {
     if (int rc = stage_points(ctx, pts, n, mem, pbuf)) return rc;
     d_pts = (const float4 *)pbuf->p;
   }
+  pt.mark("stage");
   if (int rc = slab_alloc(ctx, 12 * (size_t)n + 256, obuf)) return rc;
   int *d_nin = (int *)(obuf->p + ((12 * (size_t)n + 255) & ~(size_t)255));
   int *d_out = (mem == NDTB_MEM_DEVICE && !count_only) ? out : (int *)obuf->p;
   CU_TRY(ctx, cudaMemsetAsync(d_nin, 0, 4, ctx->stream));
   ctx->launches += launch_point_indices(m->g, d_pts, (int)n, d_out, d_nin, ctx->stream);
+  pt.mark("kernel");
   int nin = 0;
   if (mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 12 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(&nin, d_nin, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1305,7 +1387,7 @@ int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src
   MatchJob *d_job = (MatchJob *)s->p;
   double *d_part = (double *)(s->p + ((sizeof(MatchJob) + 255) & ~(size_t)255));
   double *d_out = d_part + (size_t)W * n_ctas;
-  CU_TRY(ctx, cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, h2d_small(ctx, d_job, &j, sizeof j, ctx->stream));
   CU_TRY(ctx, launch_derivatives(d_job, cfg, want_hessian != 0, n_ctas, d_part, d_out, ctx->stream));
   ctx->launches += 2;
   std::vector<double> h((size_t)W);
@@ -1335,7 +1417,7 @@ int cells_source(ndtb_ctx *ctx, const ndtb_cell *cells, int64_t n, std::unique_p
   if (int rc = slab_alloc(ctx, 256 + 72 * std::max<size_t>(ng, 1), cbuf)) return rc;
   CU_TRY(ctx, cudaMemsetAsync(cbuf->p, 0xFF, 256, ctx->stream));
   if (ng > 0) {
-    CU_TRY(ctx, cudaMemcpyAsync(cbuf->p + 256, g.data(), 72 * ng, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, h2d_small(ctx, cbuf->p + 256, g.data(), 72 * ng, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // g is a local vector
   }
   out.reset(new ndtb_map());
@@ -1449,7 +1531,7 @@ int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src,
   SlabP s;
   if (int rc = slab_alloc(ctx, c.off, s)) return rc;
   CU_TRY(ctx, cudaMemsetAsync(s->p, 0, s->bytes, st));
-  CU_TRY(ctx, cudaMemcpyAsync(s->p + o_job, &j, sizeof j, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, h2d_small(ctx, s->p + o_job, &j, sizeof j, st));
   CU_TRY(ctx, launch_covariance((MatchJob *)(s->p + o_job), 1, cfg, nullptr, (const long long *)(s->p + o_goff),
                                 (double *)(s->p + o_gt), (double *)(s->p + o_part), n_chunks, (double *)(s->p + o_cov),
                                 (int *)(s->p + o_stat), nullptr, 0, st));
@@ -1551,9 +1633,9 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
   }
   const int rc = match_batch_impl(ctx, n_pairs, tg.data(), sr.data(), T0s, nullptr, p, with_covariance && cov36s, out_mem, res, cov36s);
   pt.mark("match+cov");
-  if (rc == NDTB_OK && out_mem == NDTB_MEM_DEVICE) {
-    // outputs stay on the device and the temporary maps are released stream-ordered: no host sync needed
-  }
+  // outputs in device memory stay there and the temporary maps are released stream-ordered: no host sync needed
+  own.clear();
+  pt.mark("release maps");
   return rc;
 }
 
@@ -1605,10 +1687,10 @@ int ndtb_overlap_score_batch(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *re
   const size_t o_out = c.take(8 * (size_t)n);
   SlabP s;
   if (int rc = slab_alloc(ctx, c.off, s)) return rc;
-  CU_TRY(ctx, cudaMemcpyAsync(s->p + o_j, j.data(), sizeof(BuildJob) * j.size(), cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, h2d_small(ctx, s->p + o_j, j.data(), sizeof(BuildJob) * j.size(), st));
   const double *d_T = (const double *)T;
   if (T_mem != NDTB_MEM_DEVICE) {
-    CU_TRY(ctx, cudaMemcpyAsync(s->p + o_T, T, (size_t)T_stride_bytes * n, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, h2d_small(ctx, s->p + o_T, T, (size_t)T_stride_bytes * n, st));
     d_T = (const double *)(s->p + o_T);
   }
   double *d_out = out_mem == NDTB_MEM_DEVICE ? scores : (double *)(s->p + o_out);
@@ -1647,7 +1729,7 @@ int ndtb_transform_point_cloud(ndtb_ctx *ctx, const double *T16, const float *in
     T12[9 + r] = (float)T16[12 + r];
   }
   if (int rc = slab_alloc(ctx, sizeof T12, tbuf)) return rc;
-  CU_TRY(ctx, cudaMemcpyAsync(tbuf->p, T12, sizeof T12, cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, h2d_small(ctx, tbuf->p, T12, sizeof T12, st));
   ctx->launches += launch_transform_points(d_in, d_out, (int)n, (const float *)tbuf->p, st);
   if (out_mem != NDTB_MEM_DEVICE) {
     CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 16 * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -1672,8 +1754,8 @@ void ndtb_internal_free(ndtb_ctx *ctx, void *p) {
 int ndtb_internal_upload(ndtb_ctx *ctx, void *dst, const void *src, size_t bytes, int src_mem) {
   DeviceGuard dev_guard(ctx);
   if (!ctx) return NDTB_ERR_ARG;
-  CU_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, src_mem == NDTB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                              ctx->stream));
+  CU_TRY(ctx, src_mem == NDTB_MEM_DEVICE ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream)
+                                         : h2d_small(ctx, dst, src, bytes, ctx->stream));
   if (src_mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may reuse its buffer
   return NDTB_OK;
 }

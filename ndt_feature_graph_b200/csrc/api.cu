@@ -520,7 +520,15 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
   const int L = (int)live.size();
   if (L == 0) return NDTB_OK;
   CU_TRY(ctx, h2d_small(ctx, d_jobs, live.data(), sizeof(BuildJob) * L, st));
-  ctx->launches += launch_mark(d_jobs, L, max_pts, any_trace, st);
+  bool fast_mark = !any_trace;  // power-of-two cells, no range limit, no trace segment: k_mark<true>
+  for (const BuildJob &lj : live) {
+    for (int a = 0; a < 3; a++) {
+      int ex = 0;
+      fast_mark = fast_mark && std::frexp(lj.g.cell[a], &ex) == 0.5 && ex > -900 && ex < 900;
+    }
+    fast_mark = fast_mark && !(lj.range_limit > 0) && lj.n_seg == 0;
+  }
+  ctx->launches += launch_mark(d_jobs, L, max_pts, any_trace, fast_mark, st);
   CU_TRY(ctx, cudaGetLastError());
   std::vector<int> cnts_all(8 * (size_t)M), cnts(8 * (size_t)L);
   CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));

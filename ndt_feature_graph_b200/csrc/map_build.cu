@@ -178,28 +178,39 @@ __global__ void k_extent(const BuildJob *__restrict__ jobs, const int *__restric
   const BuildJob &j = jobs[which[blockIdx.y]];
   double *o = out + (size_t)blockIdx.y * 8;
   const double cx = o[0], cy = o[1], cz = o[2];
-  double md = 0.0;
+  // maxDist = max_i sqrt(s_i) = sqrt(max_i s_i): a correctly rounded square root is monotone, so one sqrt per warp gives
+  // the bits the reference's per-point sqrt gives
+  double ms = 0.0;
   unsigned long long kmax = 0ull, kmin = ~0ull;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.npts; i += gridDim.x * blockDim.x) {
-    const float4 p = j.pts[i];
-    if (pt_skip(p, j.range_limit, j.range_origin)) continue;
-    const double d0 = cx - (double)p.x, d1 = cy - (double)p.y, d2 = cz - (double)p.z;
-    const double dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-    md = dist > md ? dist : md;
-    const unsigned long long kk = ord_key(d2);
-    kmax = kk > kmax ? kk : kmax;
-    kmin = kk < kmin ? kk : kmin;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < j.npts; i0 += 4 * stride) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * stride;
+      p[u] = i < j.npts ? j.pts[i] : make_float4(nanf(""), 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (pt_skip(p[u], j.range_limit, j.range_origin)) continue;
+      const double d0 = cx - (double)p[u].x, d1 = cy - (double)p[u].y, d2 = cz - (double)p[u].z;
+      const double sq = d0 * d0 + d1 * d1 + d2 * d2;
+      ms = sq > ms ? sq : ms;
+      const unsigned long long kk = ord_key(d2);
+      kmax = kk > kmax ? kk : kmax;
+      kmin = kk < kmin ? kk : kmin;
+    }
   }
   for (int off = 16; off > 0; off >>= 1) {
-    const double m2 = __shfl_xor_sync(FULL, md, off);
-    md = m2 > md ? m2 : md;
+    const double m2 = __shfl_xor_sync(FULL, ms, off);
+    ms = m2 > ms ? m2 : ms;
     const unsigned long long a = __shfl_xor_sync(FULL, kmax, off), b = __shfl_xor_sync(FULL, kmin, off);
     kmax = a > kmax ? a : kmax;
     kmin = b < kmin ? b : kmin;
   }
   if ((threadIdx.x & 31) == 0) {
     unsigned long long *k = reinterpret_cast<unsigned long long *>(o);
-    atomicMax(k + 4, (unsigned long long)__double_as_longlong(md));  // md >= 0: bit pattern is monotone
+    atomicMax(k + 4, (unsigned long long)__double_as_longlong(sqrt(ms)));  // >= 0: the bit pattern is monotone
     atomicMax(k + 5, kmax);
     atomicMin(k + 6, kmin);
   }
@@ -324,9 +335,18 @@ __global__ void k_trace_fill(const BuildJob *__restrict__ jobs) {
 // ---- binning -----------------------------------------------------------------------------------------
 // Four points per thread and iteration, all loads of a stage issued before the first use: the kernel is bound by the
 // latency of the dependent mask look-up, not by bytes.
+// FAST: every map of the launch has power-of-two cell sizes, no range limit and no trace segment (the host checks) — the
+// general kernel carries the IEEE division and the square root of the range test as predicated code even where a job does
+// not need them (60 % of its issued instructions on the C2 workload, ncu source counters).
+template <bool FAST>
 __global__ void k_mark(const BuildJob *__restrict__ jobs) {
   const BuildJob &j = jobs[blockIdx.y];
   const int stride = gridDim.x * blockDim.x;
+  double inv[3] = {0, 0, 0}, half[3] = {0, 0, 0};
+  if (FAST) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) inv[a] = __drcp_rn(j.g.cell[a]), half[a] = (double)j.g.size[a] * 0.5;  // exact: power of two
+  }
   for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < j.npts; i0 += 4 * stride) {
     float4 p[4];
 #pragma unroll
@@ -339,16 +359,28 @@ __global__ void k_mark(const BuildJob *__restrict__ jobs) {
     for (int u = 0; u < 4; u++) {
       int ix, iy, iz;
       key[u] = -1, b[u] = 0, bit[u] = 0;
-      bool live = !pt_skip(p[u], j.range_limit, j.range_origin);
-      if (live && j.n_seg) {  // the end point of a ray that addPointCloud ignores is not binned either
-        const int sgi = seg_of(j, i0 + u * stride);
-        if (sgi >= 0) {
-          double dd[3], l;
-          int N;
-          live = ray_setup(j, j.seg[sgi], p[u], dd, N, l);
+      bool ok;
+      if (FAST) {
+        // same operations as voxel_axis with x / cell replaced by the exact x * (1 / cell); NaN fails the range test
+        const double v0 = __dadd_rn(floor(__dadd_rn(__dmul_rn(__dsub_rn((double)p[u].x, j.g.center[0]), inv[0]), 0.5)), half[0]);
+        const double v1 = __dadd_rn(floor(__dadd_rn(__dmul_rn(__dsub_rn((double)p[u].y, j.g.center[1]), inv[1]), 0.5)), half[1]);
+        const double v2 = __dadd_rn(floor(__dadd_rn(__dmul_rn(__dsub_rn((double)p[u].z, j.g.center[2]), inv[2]), 0.5)), half[2]);
+        ok = v0 > -2147483000.0 && v0 < 2147483000.0 && v1 > -2147483000.0 && v1 < 2147483000.0 && v2 > -2147483000.0 &&
+             v2 < 2147483000.0;
+        ix = __double2int_rz(v0), iy = __double2int_rz(v1), iz = __double2int_rz(v2);
+      } else {
+        bool live = !pt_skip(p[u], j.range_limit, j.range_origin);
+        if (live && j.n_seg) {  // the end point of a ray that addPointCloud ignores is not binned either
+          const int sgi = seg_of(j, i0 + u * stride);
+          if (sgi >= 0) {
+            double dd[3], l;
+            int N;
+            live = ray_setup(j, j.seg[sgi], p[u], dd, N, l);
+          }
         }
+        ok = live && voxel_index(j.g, (double)p[u].x, (double)p[u].y, (double)p[u].z, ix, iy, iz);
       }
-      if (live && voxel_index(j.g, (double)p[u].x, (double)p[u].y, (double)p[u].z, ix, iy, iz) && in_grid(j.g, ix, iy, iz)) {
+      if (ok && in_grid(j.g, ix, iy, iz)) {
         b[u] = sblock_id(j, ix, iy, iz), bit[u] = block_bit(ix, iy, iz);
         key[u] = b[u] >= 0 ? b[u] * 64 + bit[u] : -1;  // (outside the storage box: cannot happen, the box bounds the points)
         b[u] = b[u] >= 0 ? b[u] : 0;
@@ -445,10 +477,6 @@ __global__ void k_count(const BuildJob *__restrict__ jobs) {
 // Dropped points (key -1) sort to the end as key n_all.  Ping-pong: X = (pt_cell, seg_idx), Y = (key2, seg2); pass p reads
 // X when p is even; the ids of the first pass are implicit (iota).
 constexpr int RS_TILE = 2048, RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_PER_WARP = RS_TILE / RS_WARPS;
-__device__ __forceinline__ int rs_key(const BuildJob &j, const int *keys, int i) {
-  const int k = keys[i];
-  return k < 0 ? j.n_all : k;
-}
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const BuildJob *__restrict__ jobs, int shift, int parity) {
   const BuildJob &j = jobs[blockIdx.y];
   const int n = j.npts, tile = blockIdx.x;
@@ -458,10 +486,16 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const BuildJob *__restri
   __shared__ int hist[256];
   hist[threadIdx.x] = 0;
   __syncthreads();
+  int kk[RS_TILE / RS_THREADS];
 #pragma unroll
   for (int u = 0; u < RS_TILE / RS_THREADS; u++) {
     const int i = tile * RS_TILE + u * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&hist[(rs_key(j, keys, i) >> shift) & 255], 1);
+    kk[u] = i < n ? keys[i] : 0;
+  }
+#pragma unroll
+  for (int u = 0; u < RS_TILE / RS_THREADS; u++) {
+    const int i = tile * RS_TILE + u * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&hist[((kk[u] < 0 ? j.n_all : kk[u]) >> shift) & 255], 1);
   }
   __syncthreads();
   j.rs_hist[threadIdx.x * T + tile] = hist[threadIdx.x];
@@ -493,17 +527,32 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const BuildJob *__res
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   for (int q = threadIdx.x; q < RS_WARPS * 256; q += RS_THREADS) (&wh[0][0])[q] = 0;
-  __syncthreads();
   const int w0 = tile * RS_TILE + warp * RS_PER_WARP;
-  // (a) digit counts of every warp's contiguous slice
-  for (int u = 0; u < RS_PER_WARP / 32; u++) {
+  constexpr int U = RS_PER_WARP / 32;
+  int k[U], v[U], rank[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {  // all loads of the slice in flight together
+    const int i = w0 + u * 32 + lane;
+    k[u] = i < n ? keys[i] : 0;
+    v[u] = (i < n && !first) ? vals[i] : i;
+  }
+  __syncthreads();
+  // (a) one counting pass over the warp's contiguous slice: the running count of a digit when an element arrives, plus the
+  // equal digits in lower lanes of its chunk, is the element's stable rank among the slice's elements with that digit
+#pragma unroll
+  for (int u = 0; u < U; u++) {
     const int i = w0 + u * 32 + lane;
     const bool act = i < n;
-    const int d = act ? (rs_key(j, keys, i) >> shift) & 255 : 0;
+    const int d = ((k[u] < 0 ? j.n_all : k[u]) >> shift) & 255;
     const unsigned am = __ballot_sync(FULL, act);
+    rank[u] = 0;
     if (act) {
       const unsigned peers = __match_any_sync(am, d);
-      if (lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
+      const int leader = __ffs(peers) - 1;
+      int o = 0;
+      if (lane == leader) o = wh[warp][d], wh[warp][d] = o + __popc(peers);
+      o = __shfl_sync(peers, o, leader);
+      rank[u] = o + __popc(peers & lt);
     }
     __syncwarp();
   }
@@ -519,24 +568,16 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const BuildJob *__res
     }
   }
   __syncthreads();
-  // (c) stable scatter: slices in order, lanes in order inside a chunk
-  for (int u = 0; u < RS_PER_WARP / 32; u++) {
+  // (c) stable scatter
+#pragma unroll
+  for (int u = 0; u < U; u++) {
     const int i = w0 + u * 32 + lane;
-    const bool act = i < n;
-    const int k = act ? keys[i] : 0;
-    const int d = act ? ((k < 0 ? j.n_all : k) >> shift) & 255 : 0;
-    const unsigned am = __ballot_sync(FULL, act);
-    if (act) {
-      const unsigned peers = __match_any_sync(am, d);
-      const int leader = __ffs(peers) - 1;
-      int o = 0;
-      if (lane == leader) o = wh[warp][d], wh[warp][d] = o + __popc(peers);
-      o = __shfl_sync(peers, o, leader);
-      const int pos = o + __popc(peers & lt);
-      okeys[pos] = k;
-      ovals[pos] = first ? i : vals[i];
+    if (i < n) {
+      const int d = ((k[u] < 0 ? j.n_all : k[u]) >> shift) & 255;
+      const int pos = wh[warp][d] + rank[u];
+      okeys[pos] = k[u];
+      ovals[pos] = v[u];
     }
-    __syncwarp();
   }
 }
 // segment of every cell in the sorted order: seg_off[c] = first position, cnt[c] = number of points; counts[4] = points binned
@@ -1106,8 +1147,9 @@ int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int ma
   return 3;
 }
 static int launch_group_by_cell(const BuildJob *d_jobs, int n, int max_items, int max_cells, cudaStream_t s);
-int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, cudaStream_t s) {
-  k_mark<<<dim3(chunks_for(max_pts, NDTB_PTS_PER_CTA), n), 256, 0, s>>>(d_jobs);
+int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, bool fast, cudaStream_t s) {
+  if (fast && !trace) k_mark<true><<<dim3(chunks_for(max_pts, NDTB_PTS_PER_CTA), n), 256, 0, s>>>(d_jobs);
+  else k_mark<false><<<dim3(chunks_for(max_pts, NDTB_PTS_PER_CTA), n), 256, 0, s>>>(d_jobs);
   if (trace) {
     k_trace_count<<<dim3(chunks_for(max_pts, 128), n), 128, 0, s>>>(d_jobs);
     k_rayscan<<<n, 1024, 0, s>>>(d_jobs);

@@ -82,7 +82,7 @@ int centroid_record_doubles();
 // centroid_chunk_points() points)
 int launch_guess(const BuildJob *d_jobs, const int *d_which, int n_which, int max_pts, const long long *d_rec_off, double *d_recs,
                  double *d_out, cudaStream_t s);
-int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, cudaStream_t s);
+int launch_mark(const BuildJob *d_jobs, int n, int max_pts, bool trace, bool fast, cudaStream_t s);
 // visit lists of the ray trace: d_vjobs = the jobs with the per-point arrays replaced by the per-visit arrays
 int launch_trace_lists(const BuildJob *d_jobs, const BuildJob *d_vjobs, int n, int max_pts, int max_vis, int max_ntb, int max_cells,
                        cudaStream_t s);

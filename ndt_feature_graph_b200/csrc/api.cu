@@ -615,7 +615,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
   ctx->launches += launch_cells(d_jobs, L, max_pts, max_ntb, max_cells, st);
   CU_TRY(ctx, cudaGetLastError());
   pt.mark("cells");
-  ctx->launches += launch_gview(d_jobs, L, max_ntb, st);
+  ctx->launches += launch_gview(d_jobs, L, max_ntb, max_cells, st);
   CU_TRY(ctx, cudaGetLastError());
   CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -1297,7 +1297,7 @@ int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells,
   CU_TRY(ctx, cudaMemsetAsync(j.table, 0xFF, sizeof(HashEntry) * (size_t)tsize, st));
   CU_TRY(ctx, h2d_small(ctx, d_job, &j, sizeof j, st));
   ctx->launches += launch_from_cells_place(d_job, d_cells, (int)n, d_vox, st);
-  ctx->launches += launch_gview(d_job, 1, std::max(ntb, 1), st);
+  ctx->launches += launch_gview(d_job, 1, std::max(ntb, 1), std::max(n_all, 1), st);
   CU_TRY(ctx, cudaMemcpyAsync(cnts, j.counts, 32, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
   m->s_blocks = s_b, m->s_cells = s_c;

@@ -948,13 +948,20 @@ __global__ void k_gfill(const BuildJob *__restrict__ jobs) {
     for (; m; m &= m - 1ull, c++) {
       const int bit = __ffsll((long long)m) - 1;
       if (!(gm >> bit & 1ull)) continue;
-      double *o = j.gcell + (size_t)gs * GC;
-      o[0] = j.cmean[(size_t)c * 3], o[1] = j.cmean[(size_t)c * 3 + 1], o[2] = j.cmean[(size_t)c * 3 + 2];
-      const double *cv = j.ccov + (size_t)c * 9;
-      o[3] = cv[0], o[4] = cv[1], o[5] = cv[2], o[6] = cv[4], o[7] = cv[5], o[8] = cv[8];
-      j.g2c[gs] = c;
+      j.g2c[gs] = c;  // the record itself is copied by k_gcopy, one thread per double
       gs++;
     }
+  }
+}
+// compact Gaussian view: gcell[g] = mean(3) + upper triangle of cov(6) of cell g2c[g]; one thread per output double
+__global__ void k_gcopy(const BuildJob *__restrict__ jobs) {
+  const BuildJob &j = jobs[blockIdx.y];
+  const int total = j.counts[2] * GC;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int g = e / GC, q = e - g * GC;
+    const int c = j.g2c[g];
+    const int cq = q == 3 ? 0 : (q == 4 ? 1 : (q == 5 ? 2 : (q == 6 ? 4 : (q == 7 ? 5 : 8))));
+    j.gcell[e] = q < 3 ? j.cmean[(size_t)c * 3 + q] : j.ccov[(size_t)c * 9 + cq];
   }
 }
 
@@ -1199,10 +1206,11 @@ int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int ma
   k_eigen_hard<<<dim3(chunks_for(max_cells / 16 + 1, 128), n), 128, 0, s>>>(d_jobs);
   return ns + 4;
 }
-int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s) {
+int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, int max_cells, cudaStream_t s) {
   k_gscan<<<n, 1024, 0, s>>>(d_jobs);
   k_gfill<<<dim3(chunks_for(max_ntb, 128), n), 128, 0, s>>>(d_jobs);
-  return 2;
+  k_gcopy<<<dim3(chunks_for(max_cells * GC, 1024), n), 256, 0, s>>>(d_jobs);
+  return 3;
 }
 int launch_blockscan(const BuildJob *d_jobs, int n, cudaStream_t s) {
   k_blockscan<<<n, 1024, 0, s>>>(d_jobs);

@@ -90,7 +90,7 @@ int launch_transform_points(const float4 *d_in, float4 *d_out, int n, const floa
 int launch_cells(const BuildJob *d_jobs, int n, int max_pts, int max_ntb, int max_cells, cudaStream_t s);
 int sort_passes(int max_cells);  // 8-bit radix passes needed for cell ids 0..max_cells
 int sort_tile_points();  // points per radix-sort tile (sizing of BuildJob::rs_hist: 256 ints per tile)
-int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, cudaStream_t s);
+int launch_gview(const BuildJob *d_jobs, int n, int max_ntb, int max_cells, cudaStream_t s);
 int launch_blockscan(const BuildJob *d_jobs, int n, cudaStream_t s);
 int launch_export(const BuildJob *d_job, int ntb, ndtb_cell *d_out, cudaStream_t s);
 int launch_from_cells_voxel(const BuildJob *d_job, const ndtb_cell *d_cells, int n, int use_idx, int *d_vox, int *d_err,

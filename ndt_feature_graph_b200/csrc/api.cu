@@ -11,6 +11,9 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -59,6 +62,15 @@ struct ndtb_ctx {
   // small host->device uploads (job descriptors, poses, single scans) bypass the copy engine: see h2d_small
   static constexpr int STG_SEGS = 8;
   static constexpr size_t STG_SEG_BYTES = (size_t)4 << 20, STG_MAX = (size_t)1 << 20;
+  // slab cache: see slab_alloc
+  struct CachedSlab {
+    char *p;
+    uint64_t stamp;
+  };
+  std::mutex cache_mu;
+  std::unordered_map<size_t, std::vector<CachedSlab>> slab_cache;  // by capacity class
+  size_t cached_bytes = 0, cache_limit = (size_t)16 << 30;
+  uint64_t cache_clock = 0;
   char *stg_host = nullptr, *stg_dev = nullptr;
   cudaEvent_t stg_ev[STG_SEGS] = {};
   bool stg_used[STG_SEGS] = {};
@@ -92,6 +104,22 @@ struct DeviceGuard {
 };
 
 namespace {
+
+// NDTB_SLOWLOG=<ms>: calls of ndtb_register_scans slower than that print where their host time went (stderr)
+struct SlowLog {
+  double alloc_ms = 0, sync_ms = 0, up_ms = 0, enq_ms = 0;
+  int allocs = 0, syncs = 0;
+};
+thread_local SlowLog g_slow;
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline cudaError_t timed_sync(cudaStream_t st) {
+  const double t0 = now_ms();
+  const cudaError_t e = cudaStreamSynchronize(st);
+  g_slow.sync_ms += now_ms() - t0, g_slow.syncs++;
+  return e;
+}
 
 // ---- small uploads without the copy engine -----------------------------------------------------------------------
 // The H2D copy engine serves its queue in submission order ACROSS streams: a 470 KB job-descriptor upload issued while
@@ -152,21 +180,85 @@ struct PhaseTimer {
   void mark(const char *label);
 };
 
-struct Slab {  // one stream-ordered device allocation shared by the maps of a batch
+// Slabs: stream-ordered device allocations shared by the maps of a batch.  A released slab goes to a per-context cache
+// keyed by its capacity class (sizes rounded up to 1/8 octave) and the next request of that class takes it back: every
+// use of a context's slabs is ordered on the context's stream (the copy and covariance streams join it through events), so
+// a block released on the host may be handed to work that is enqueued later.  CUDA's own stream-ordered pool sits below
+// the cache and only sees the misses: in steady state it re-mapped physical memory when three contexts kept releasing
+// and requesting ~2 GB slabs of slightly different sizes — single cudaMallocFromPoolAsync calls of 0.4-2.4 s, during which
+// the other contexts' synchronisations stalled as well (measured with NDTB_SLOWLOG on the B200 box).
+struct Slab {
   ndtb_ctx *ctx;
   char *p = nullptr;
-  size_t bytes = 0;
+  size_t bytes = 0;  // requested
+  size_t cap = 0;    // capacity class actually allocated
   Slab(ndtb_ctx *c) : ctx(c) {}
-  ~Slab() {
-    if (p) cudaFreeAsync(p, ctx->stream);
-  }
+  ~Slab();
 };
 using SlabP = std::shared_ptr<Slab>;
+
+inline size_t slab_class(size_t b) {
+  if (b <= 4096) return 4096;
+  const int e = 63 - __builtin_clzll((unsigned long long)b);
+  const size_t step = (size_t)1 << (e - 3);
+  return (b + step - 1) & ~(step - 1);
+}
+Slab::~Slab() {
+  if (!p) return;
+  std::vector<char *> evict;
+  {
+    std::lock_guard<std::mutex> lk(ctx->cache_mu);
+    ctx->slab_cache[cap].push_back({p, ++ctx->cache_clock});
+    ctx->cached_bytes += cap;
+    while (ctx->cached_bytes > ctx->cache_limit) {  // evict the blocks released longest ago
+      size_t best_cls = 0, best_i = 0;
+      uint64_t best = ~0ull;
+      for (auto &kv : ctx->slab_cache)
+        for (size_t i = 0; i < kv.second.size(); i++)
+          if (kv.second[i].stamp < best) best = kv.second[i].stamp, best_cls = kv.first, best_i = i;
+      if (best == ~0ull) break;
+      auto &v = ctx->slab_cache[best_cls];
+      evict.push_back(v[best_i].p);
+      v.erase(v.begin() + (long)best_i);
+      ctx->cached_bytes -= best_cls;
+    }
+  }
+  for (char *q : evict) cudaFreeAsync(q, ctx->stream);
+}
 
 int slab_alloc(ndtb_ctx *ctx, size_t bytes, SlabP &out) {
   out = std::make_shared<Slab>(ctx);
   out->bytes = bytes ? bytes : 256;
-  CU_TRY(ctx, cudaMallocFromPoolAsync((void **)&out->p, out->bytes, ctx->pool, ctx->stream));
+  out->cap = slab_class(out->bytes);
+  {
+    std::lock_guard<std::mutex> lk(ctx->cache_mu);
+    auto it = ctx->slab_cache.find(out->cap);
+    if (it != ctx->slab_cache.end() && !it->second.empty()) {
+      out->p = it->second.back().p;
+      it->second.pop_back();
+      ctx->cached_bytes -= out->cap;
+      return NDTB_OK;
+    }
+  }
+  const double t0 = now_ms();
+  cudaError_t e = cudaMallocFromPoolAsync((void **)&out->p, out->cap, ctx->pool, ctx->stream);
+  if (e != cudaSuccess) {  // out of memory with blocks parked in the cache: release them and try once more
+    cudaGetLastError();
+    std::vector<char *> all;
+    {
+      std::lock_guard<std::mutex> lk(ctx->cache_mu);
+      for (auto &kv : ctx->slab_cache) {
+        for (auto &c : kv.second) all.push_back(c.p);
+        kv.second.clear();
+      }
+      ctx->cached_bytes = 0;
+    }
+    for (char *q : all) cudaFreeAsync(q, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    out->p = nullptr;
+    CU_TRY(ctx, cudaMallocFromPoolAsync((void **)&out->p, out->cap, ctx->pool, ctx->stream));
+  }
+  g_slow.alloc_ms += now_ms() - t0, g_slow.allocs++;
   return NDTB_OK;
 }
 
@@ -332,7 +424,7 @@ int define_grids(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const std::
                                   (double *)(s->p + o_rec), (double *)(s->p + o_gs), st);
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaMemcpyAsync(gs.data(), s->p + o_gs, 64 * (size_t)W, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, timed_sync(st));
     auto unkey = [](double bits) {
       unsigned long long k;
       std::memcpy(&k, &bits, 8);
@@ -532,7 +624,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
   CU_TRY(ctx, cudaGetLastError());
   std::vector<int> cnts_all(8 * (size_t)M), cnts(8 * (size_t)L);
   CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));
-  CU_TRY(ctx, cudaStreamSynchronize(st));
+  CU_TRY(ctx, timed_sync(st));
   for (int l = 0; l < L; l++) std::memcpy(&cnts[8 * l], &cnts_all[8 * (size_t)live_idx[l]], 32);
   pt.mark("mark+scan");
 
@@ -618,7 +710,7 @@ int build_batch_slice(ndtb_ctx *ctx, const std::vector<ndtb_map *> &maps, const 
   ctx->launches += launch_gview(d_jobs, L, max_ntb, max_cells, st);
   CU_TRY(ctx, cudaGetLastError());
   CU_TRY(ctx, cudaMemcpyAsync(cnts_all.data(), s_b->p + o_counts_all, 32 * (size_t)M, cudaMemcpyDeviceToHost, st));
-  CU_TRY(ctx, cudaStreamSynchronize(st));
+  CU_TRY(ctx, timed_sync(st));
   for (int l = 0; l < L; l++) std::memcpy(&cnts[8 * l], &cnts_all[8 * (size_t)live_idx[l]], 32);
   pt.mark("gview");
   for (int l = 0; l < L; l++) {
@@ -750,7 +842,7 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
   if (budget > 0) {
     int n_unf = 0;
     CU_TRY(ctx, cudaMemcpyAsync(&n_unf, d_unf, 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, timed_sync(st));
     if (n_unf > 0) {
       if (do_cov) {
         if (!ctx->aux_stream) {
@@ -795,7 +887,7 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
   }
   if (out_mem != NDTB_MEM_DEVICE) {
     CU_TRY(ctx, cudaMemcpyAsync(res, d_res, sizeof(ndtb_result) * n, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, timed_sync(st));
   }
   return NDTB_OK;
 }
@@ -857,6 +949,11 @@ int ndtb_ctx_create(int device, void *stream, ndtb_ctx **out) {
   }
   uint64_t thr = UINT64_MAX;
   cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) c->cache_limit = total_b / 8;  // released slabs parked per context
+    if (const char *e = std::getenv("NDTB_SLAB_CACHE_MB")) c->cache_limit = (size_t)std::atoll(e) << 20;
+  }
   if (match_kernel_prepare(c->smem_optin) != cudaSuccess) {
     cudaMemPoolDestroy(c->pool);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -872,6 +969,10 @@ void ndtb_ctx_destroy(ndtb_ctx *ctx) {
   if (!ctx) return;
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream), cudaStreamDestroy(ctx->copy_stream);
+  for (auto &kv : ctx->slab_cache)
+    for (auto &c : kv.second) cudaFreeAsync(c.p, ctx->stream);
+  ctx->slab_cache.clear();
+  cudaStreamSynchronize(ctx->stream);
   if (ctx->stg_host) {
     for (cudaEvent_t e : ctx->stg_ev)
       if (e) cudaEventDestroy(e);
@@ -889,7 +990,7 @@ void ndtb_ctx_destroy(ndtb_ctx *ctx) {
 int ndtb_ctx_synchronize(ndtb_ctx *ctx) {
   DeviceGuard dev_guard(ctx);
   if (!ctx) return NDTB_ERR_ARG;
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, timed_sync(ctx->stream));
   return NDTB_OK;
 }
 int64_t ndtb_ctx_launch_count(const ndtb_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -901,7 +1002,7 @@ int ndtb_ctx_enable_timing(ndtb_ctx *ctx, int on) {
 int ndtb_ctx_match_time(ndtb_ctx *ctx, double *ms, int64_t *launches) {
   DeviceGuard dev_guard(ctx);
   if (!ctx || !ms) return NDTB_ERR_ARG;
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, timed_sync(ctx->stream));
   double tot = 0;
   for (auto &pr : ctx->timed) {
     float t = 0;
@@ -917,7 +1018,7 @@ int ndtb_ctx_match_time(ndtb_ctx *ctx, double *ms, int64_t *launches) {
 int ndtb_ctx_build_time(ndtb_ctx *ctx, double *ms, int64_t *calls) {
   DeviceGuard dev_guard(ctx);
   if (!ctx || !ms) return NDTB_ERR_ARG;
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, timed_sync(ctx->stream));
   double tot = 0;
   for (auto &pr : ctx->timed_build) {
     float t = 0;
@@ -1204,12 +1305,14 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
     for (auto &e : tev) cudaEventCreate(&e);
     cudaEventRecord(tev[0], cs);
   }
+  const double t_enq = now_ms();
   for (int k = 0; k < n_chunks; k++) {
     for (int64_t i = cbeg[k]; i < cbeg[k + 1]; i++)
       if (n_pts[i] > 0) CU_TRY(ctx, cudaMemcpyAsync(big->p + off[i], pts[i], 16 * (size_t)n_pts[i], cudaMemcpyHostToDevice, cs));
     if (n_chunks > 1) CU_TRY(ctx, cudaEventRecord(ctx->copy_events[k], cs));
     if (prof_copies) cudaEventRecord(tev[(size_t)k + 1], cs);
   }
+  g_slow.enq_ms += now_ms() - t_enq;
   pt.mark("enqueue H2D");
   int rc = NDTB_OK;
   for (int k = 0; k < n_chunks && rc == NDTB_OK; k++) {
@@ -1277,7 +1380,7 @@ int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells,
   int cnts[8], err = 0;
   CU_TRY(ctx, cudaMemcpyAsync(cnts, j.counts, 32, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(ctx, cudaStreamSynchronize(st));
+  CU_TRY(ctx, timed_sync(st));
   if (err) return NDTB_ERR_ARG;  // a cell outside the grid (the CPU restatement returns -1)
   const int n_all = cnts[0], ntb = cnts[1];
   int tsize = 2;
@@ -1299,7 +1402,7 @@ int ndtb_map_from_cells(ndtb_map *m, const ndtb_grid *g, const ndtb_cell *cells,
   ctx->launches += launch_from_cells_place(d_job, d_cells, (int)n, d_vox, st);
   ctx->launches += launch_gview(d_job, 1, std::max(ntb, 1), std::max(n_all, 1), st);
   CU_TRY(ctx, cudaMemcpyAsync(cnts, j.counts, 32, cudaMemcpyDeviceToHost, st));
-  CU_TRY(ctx, cudaStreamSynchronize(st));
+  CU_TRY(ctx, timed_sync(st));
   m->s_blocks = s_b, m->s_cells = s_c;
   m->amask = j.amask, m->abase = j.abase, m->tb_list = j.tb_list, m->counts = j.counts;
   m->n_all = n_all, m->ntb = ntb, m->ng = cnts[2], m->ngb = cnts[3];
@@ -1337,7 +1440,7 @@ int64_t ndtb_map_export_cells(const ndtb_map *m, ndtb_cell *out, int64_t cap, in
   ctx->launches += launch_export(d_job, m->ntb, (ndtb_cell *)tmp->p, ctx->stream);
   std::vector<ndtb_cell> h((size_t)m->n_all);
   CU_TRY(ctx, cudaMemcpyAsync(h.data(), tmp->p, sizeof(ndtb_cell) * (size_t)m->n_all, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, timed_sync(ctx->stream));
   std::vector<std::pair<int64_t, int>> ord;
   for (int i = 0; i < m->n_all; i++) {
     if (gaussian_only && !h[i].has_gaussian) continue;
@@ -1373,7 +1476,7 @@ int64_t ndtb_map_point_indices(const ndtb_map *m, const float *pts, int64_t n, i
   int nin = 0;
   if (mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 12 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(&nin, d_nin, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, timed_sync(ctx->stream));
   return nin;
 }
 
@@ -1400,7 +1503,7 @@ int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src
   ctx->launches += 2;
   std::vector<double> h((size_t)W);
   CU_TRY(ctx, cudaMemcpyAsync(h.data(), d_out, 8 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, timed_sync(ctx->stream));
   out43[0] = h[0];
   for (int i = 0; i < 6; i++) out43[1 + i] = h[ACC_G + i];
   for (int a = 0; a < 6; a++)
@@ -1426,7 +1529,7 @@ int cells_source(ndtb_ctx *ctx, const ndtb_cell *cells, int64_t n, std::unique_p
   CU_TRY(ctx, cudaMemsetAsync(cbuf->p, 0xFF, 256, ctx->stream));
   if (ng > 0) {
     CU_TRY(ctx, h2d_small(ctx, cbuf->p + 256, g.data(), 72 * ng, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // g is a local vector
+    CU_TRY(ctx, timed_sync(ctx->stream));  // g is a local vector
   }
   out.reset(new ndtb_map());
   ndtb_map *m = out.get();
@@ -1547,7 +1650,7 @@ int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src,
   int status = 0;
   CU_TRY(ctx, cudaMemcpyAsync(cov36, s->p + o_cov, 288, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaMemcpyAsync(&status, s->p + o_stat, 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(ctx, cudaStreamSynchronize(st));
+  CU_TRY(ctx, timed_sync(st));
   return status;
 }
 
@@ -1605,6 +1708,9 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
   if (n_pairs == 0) return NDTB_OK;
   if (!tgt_pts || !n_tgt || !src_pts || !n_src || !T0s || !res) return NDTB_ERR_ARG;
   PhaseTimer pt0(ctx, "register_scans");
+  static const double slow_ms = std::getenv("NDTB_SLOWLOG") ? std::atof(std::getenv("NDTB_SLOWLOG")) : 0.0;
+  g_slow = SlowLog();
+  const double t_call = now_ms();
   std::vector<std::unique_ptr<ndtb_map>> own((size_t)(2 * n_pairs));
   std::vector<ndtb_map *> maps((size_t)(2 * n_pairs));
   std::vector<const float *> pts((size_t)(2 * n_pairs));
@@ -1628,6 +1734,8 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
   if (int rc = ndtb_map_build_batch(ctx, 2 * n_pairs, maps.data(), pts.data(), npts.data(), range_limit, in_mem, 0xffffffffu, 255.f))
     return rc;
   pt.mark("build_batch");
+  const double t_built = now_ms();
+  const SlowLog at_build = g_slow;
   std::vector<const ndtb_map *> tg((size_t)n_pairs), sr((size_t)n_pairs);
   for (int64_t e = 0; e < n_pairs; e++) {
     tg[e] = maps[2 * e], sr[e] = maps[2 * e + 1];
@@ -1642,8 +1750,16 @@ int ndtb_register_scans(ndtb_ctx *ctx, int64_t n_pairs, const float *const *tgt_
   const int rc = match_batch_impl(ctx, n_pairs, tg.data(), sr.data(), T0s, nullptr, p, with_covariance && cov36s, out_mem, res, cov36s);
   pt.mark("match+cov");
   // outputs in device memory stay there and the temporary maps are released stream-ordered: no host sync needed
+  const double t_matched = now_ms();
   own.clear();
   pt.mark("release maps");
+  if (slow_ms > 0 && now_ms() - t_call > slow_ms)
+    std::fprintf(stderr,
+                 "[ndtb slow] register_scans %.1f ms: build %.1f (alloc %.1f in %d, sync %.1f in %d, enqueue H2D %.1f) match %.1f "
+                 "(alloc %.1f, sync %.1f in %d) release %.1f\n",
+                 now_ms() - t_call, t_built - t_call, at_build.alloc_ms, at_build.allocs, at_build.sync_ms, at_build.syncs,
+                 at_build.enq_ms, t_matched - t_built, g_slow.alloc_ms - at_build.alloc_ms, g_slow.sync_ms - at_build.sync_ms,
+                 g_slow.syncs - at_build.syncs, now_ms() - t_matched);
   return rc;
 }
 
@@ -1706,7 +1822,7 @@ int ndtb_overlap_score_batch(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *re
   CU_TRY(ctx, cudaGetLastError());
   if (out_mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaMemcpyAsync(scores, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
   // the job table and a host T are pageable stack / vector memory: they must have been consumed before returning
-  CU_TRY(ctx, cudaStreamSynchronize(st));
+  CU_TRY(ctx, timed_sync(st));
   return NDTB_OK;
 }
 
@@ -1741,9 +1857,9 @@ int ndtb_transform_point_cloud(ndtb_ctx *ctx, const double *T16, const float *in
   ctx->launches += launch_transform_points(d_in, d_out, (int)n, (const float *)tbuf->p, st);
   if (out_mem != NDTB_MEM_DEVICE) {
     CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 16 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, timed_sync(st));
   } else {
-    CU_TRY(ctx, cudaStreamSynchronize(st));  // T12 is a stack array: the copy must have been consumed before returning
+    CU_TRY(ctx, timed_sync(st));  // T12 is a stack array: the copy must have been consumed before returning
   }
   return NDTB_OK;
 }
@@ -1764,7 +1880,7 @@ int ndtb_internal_upload(ndtb_ctx *ctx, void *dst, const void *src, size_t bytes
   if (!ctx) return NDTB_ERR_ARG;
   CU_TRY(ctx, src_mem == NDTB_MEM_DEVICE ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream)
                                          : h2d_small(ctx, dst, src, bytes, ctx->stream));
-  if (src_mem != NDTB_MEM_DEVICE) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may reuse its buffer
+  if (src_mem != NDTB_MEM_DEVICE) CU_TRY(ctx, timed_sync(ctx->stream));  // the caller may reuse its buffer
   return NDTB_OK;
 }
 

@@ -307,6 +307,34 @@ int64_t ndtb_edge_msg_pack(uint32_t ref_idx, uint32_t mov_idx, const double *T16
 /* msgToEdge (ndtgraph_conversion.h:104-145) */
 int ndtb_edge_msg_unpack(const uint8_t *buf, int64_t len, uint32_t *ref_idx, uint32_t *mov_idx, double *T16, double *cov9,
                          double *cov36, int32_t *has_cov36, double *score);
+/* The whole-graph message, NDTGraphToMsg / msgToNDTGraph (ndtgraph_conversion.h:59-83,189-216; ndt_feature/msg/NDTGraphMsg.msg,
+ * NDTNodeMsg.msg, NDTFeatureFuserHMTMsg.msg), composed from its parts.  Every *_pack returns the message length (bytes are
+ * written only when cap suffices) or < 0; every *_unpack reports offsets into the caller's buffer.
+ * ndt_map/NDTMapMsg is an upstream perception_oru type that the reference does not vendor: its field order is restated from
+ * the published message definitions (lslgeneric::toMessage writes the Gaussian cells; fromMessage re-inserts each cell at the
+ * voxel of its mean — ndtb_map_from_cells with use_idx = 0).  cells: all cells of a map (ndtb_map_export_cells). */
+int64_t ndtb_map_msg_pack(uint32_t seq, uint32_t sec, uint32_t nsec, const char *frame_id, const ndtb_grid *g, const ndtb_cell *cells,
+                          int64_t n_cells, uint8_t *out, int64_t cap);
+int ndtb_map_msg_unpack(const uint8_t *buf, int64_t len, uint32_t *stamp3, char *frame_id, int32_t frame_cap, ndtb_grid *g,
+                        ndtb_cell *cells, int64_t cells_cap, int64_t *n_cells, int64_t *consumed);
+typedef struct ndtb_node_fields { /* NDTNodeMsg + its NDTFeatureFuserHMTMsg without the map (poses column-major 4x4) */
+  double Tnow[16], Tlast_fuse[16], Todom[16]; /* fuserHMTToMsg, ndtgraph_conversion.h:36-45 */
+  uint32_t ctr;
+  uint32_t nb_updates;                        /* nodeToMsg, :47-57 */
+  double T[16];
+  double cov9[9];                             /* row-major 3x3 */
+  double Tlocal_odom[16], Tlocal_fuse[16];
+  double time_last_update;
+} ndtb_node_fields;
+int64_t ndtb_node_msg_pack(const ndtb_node_fields *f, const uint8_t *map_msg, int64_t map_len, uint8_t *out, int64_t cap);
+int ndtb_node_msg_unpack(const uint8_t *buf, int64_t len, ndtb_node_fields *f, int64_t *map_off, int64_t *map_len, int64_t *consumed);
+int64_t ndtb_graph_msg_pack(uint32_t seq, uint32_t sec, uint32_t nsec, const char *frame_id, const double *sensor_pose16,
+                            const double *Tnow16, double distance_moved, int64_t n_nodes, const uint8_t *const *node_msgs,
+                            const int64_t *node_lens, int64_t n_edges, const uint8_t *const *edge_msgs, const int64_t *edge_lens,
+                            uint8_t *out, int64_t cap);
+int ndtb_graph_msg_unpack(const uint8_t *buf, int64_t len, uint32_t *stamp3, char *frame_id, int32_t frame_cap, double *sensor_pose16,
+                          double *Tnow16, double *distance_moved, int64_t *n_nodes, int64_t *node_off, int64_t *node_len,
+                          int64_t nodes_cap, int64_t *n_edges, int64_t *edge_off, int64_t *edge_len, int64_t edges_cap);
 /* saveAffine3d / loadAffine3d of NDTFeatureNode::save / load (ndt_feature_node.h:100-152): the boost text archives
  * mapping{k}.T, ...local_odom.T, ...local_fuse.T the reference ships (byte-compatible) */
 int ndtb_pose_archive_write(const char *path, const double *T16);

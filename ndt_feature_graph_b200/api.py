@@ -163,6 +163,13 @@ def load_library():
         "ndtb_overlap_score_batch": (C.c_int, [vp, i64, vp, vp, vp, i64, C.c_int, C.c_int, vp]),
         "ndtb_edge_msg_pack": (i64, [C.c_uint32, C.c_uint32, vp, vp, vp, dbl, vp, i64]),
         "ndtb_edge_msg_unpack": (C.c_int, [vp, i64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp, vp, vp, C.POINTER(C.c_int32), C.POINTER(dbl)]),
+        "ndtb_map_msg_pack": (i64, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, vp, vp, i64, vp, i64]),
+        "ndtb_map_msg_unpack": (C.c_int, [vp, i64, vp, C.c_char_p, C.c_int32, vp, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
+        "ndtb_node_msg_pack": (i64, [vp, vp, i64, vp, i64]),
+        "ndtb_node_msg_unpack": (C.c_int, [vp, i64, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "ndtb_graph_msg_pack": (i64, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, vp, vp, dbl, i64, vp, vp, i64, vp, vp, vp, i64]),
+        "ndtb_graph_msg_unpack": (C.c_int, [vp, i64, vp, C.c_char_p, C.c_int32, vp, vp, C.POINTER(dbl), C.POINTER(i64), vp, vp, i64,
+                                            C.POINTER(i64), vp, vp, i64]),
         "ndtb_pose_archive_write": (C.c_int, [C.c_char_p, vp]),
         "ndtb_pose_archive_read": (C.c_int, [C.c_char_p, vp]),
         "ndtb_eval_string": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int32]),
@@ -381,6 +388,107 @@ def edge_msg_unpack(data):
     if rc != 0:
         raise NdtbError("malformed NDTEdgeMsg")
     return a.value, b.value, T.reshape(4, 4).T.copy(), c3.reshape(3, 3), (c6.reshape(6, 6) if has.value else None), s.value
+
+
+class NodeFields(C.Structure):
+    """ndtb_node_fields: NDTNodeMsg + NDTFeatureFuserHMTMsg without the map (poses column-major)."""
+    _fields_ = [("Tnow", C.c_double * 16), ("Tlast_fuse", C.c_double * 16), ("Todom", C.c_double * 16), ("ctr", C.c_uint32),
+                ("nb_updates", C.c_uint32), ("T", C.c_double * 16), ("cov9", C.c_double * 9), ("Tlocal_odom", C.c_double * 16),
+                ("Tlocal_fuse", C.c_double * 16), ("time_last_update", C.c_double)]
+
+    POSES = ("Tnow", "Tlast_fuse", "Todom", "T", "Tlocal_odom", "Tlocal_fuse")
+
+    @classmethod
+    def make(cls, cov=None, ctr=0, nb_updates=0, time_last_update=0.0, **poses):
+        f = cls()
+        for k in cls.POSES:
+            getattr(f, k)[:] = _cm(poses.get(k, np.eye(4))).tolist()
+        f.cov9[:] = np.ascontiguousarray(np.eye(3) if cov is None else cov, dtype=np.float64).ravel().tolist()
+        f.ctr, f.nb_updates, f.time_last_update = ctr, nb_updates, time_last_update
+        return f
+
+    def pose(self, k):
+        return np.array(getattr(self, k)[:]).reshape(4, 4).T.copy()
+
+
+def _sized(call):
+    n = call(None, 0)
+    if n < 0:
+        raise NdtbError("cannot pack message")
+    buf = np.zeros(n, np.uint8)
+    call(buf.ctypes.data, n)
+    return buf.tobytes()
+
+
+def map_msg_pack(grid, cells, frame_id="/world", stamp=(0, 0, 0)):
+    """ndt_map/NDTMapMsg of lslgeneric::toMessage [upstream] from a map's grid and ALL its cells (Gaussian cells are written)."""
+    L = load_library()
+    cells = np.ascontiguousarray(cells, dtype=CELL_DTYPE)
+    return _sized(lambda p, n: L.ndtb_map_msg_pack(stamp[0], stamp[1], stamp[2], frame_id.encode(), C.byref(grid), cells.ctypes.data,
+                                                   len(cells), p, n))
+
+
+def map_msg_unpack(data):
+    """-> (grid, Gaussian cells without voxel indices: insert with from_cells(use_idx=False), frame_id, stamp, bytes consumed)"""
+    L = load_library()
+    buf = np.frombuffer(data, np.uint8)
+    g, n, used = Grid(), C.c_int64(), C.c_int64()
+    st, frame = (C.c_uint32 * 3)(), C.create_string_buffer(256)
+    if L.ndtb_map_msg_unpack(buf.ctypes.data, len(buf), st, frame, 256, C.byref(g), None, 0, C.byref(n), C.byref(used)) != 0:
+        raise NdtbError("malformed NDTMapMsg")
+    cells = np.zeros(max(n.value, 1), CELL_DTYPE)
+    L.ndtb_map_msg_unpack(buf.ctypes.data, len(buf), st, frame, 256, C.byref(g), cells.ctypes.data, len(cells), C.byref(n), C.byref(used))
+    return g, cells[: n.value], frame.value.decode(), tuple(st), used.value
+
+
+def node_msg_pack(fields, map_msg):
+    """ndt_feature/NDTNodeMsg (nodeToMsg, ndtgraph_conversion.h:47-57)."""
+    L = load_library()
+    m = np.frombuffer(map_msg, np.uint8)
+    return _sized(lambda p, n: L.ndtb_node_msg_pack(C.byref(fields), m.ctypes.data, len(m), p, n))
+
+
+def node_msg_unpack(data):
+    """-> (NodeFields, NDTMapMsg bytes, bytes consumed) (msgToNode, ndtgraph_conversion.h:147-187)"""
+    L = load_library()
+    buf = np.frombuffer(data, np.uint8)
+    f, mo, ml, used = NodeFields(), C.c_int64(), C.c_int64(), C.c_int64()
+    if L.ndtb_node_msg_unpack(buf.ctypes.data, len(buf), C.byref(f), C.byref(mo), C.byref(ml), C.byref(used)) != 0:
+        raise NdtbError("malformed NDTNodeMsg")
+    return f, bytes(data[mo.value: mo.value + ml.value]), used.value
+
+
+def graph_msg_pack(sensor_pose, Tnow, distance_moved, node_msgs, edge_msgs, frame_id="/world", stamp=(0, 0, 0)):
+    """ndt_feature/NDTGraphMsg (NDTGraphToMsg, ndtgraph_conversion.h:59-83)."""
+    L = load_library()
+    sp, tn = _cm(sensor_pose), _cm(Tnow)
+    nb = [np.frombuffer(m, np.uint8) for m in node_msgs]
+    eb = [np.frombuffer(m, np.uint8) for m in edge_msgs]
+    npp = (C.c_void_p * max(len(nb), 1))(*[b.ctypes.data for b in nb])
+    epp = (C.c_void_p * max(len(eb), 1))(*[b.ctypes.data for b in eb])
+    nl = np.array([len(b) for b in nb] or [0], np.int64)
+    el = np.array([len(b) for b in eb] or [0], np.int64)
+    return _sized(lambda p, n: L.ndtb_graph_msg_pack(stamp[0], stamp[1], stamp[2], frame_id.encode(), sp.ctypes.data, tn.ctypes.data,
+                                                     float(distance_moved), len(nb), npp, nl.ctypes.data, len(eb), epp, el.ctypes.data, p, n))
+
+
+def graph_msg_unpack(data):
+    """-> dict(sensor_pose, Tnow, distance_moved, nodes=[NDTNodeMsg bytes], edges=[NDTEdgeMsg bytes], frame_id, stamp)
+    (msgToNDTGraph, ndtgraph_conversion.h:189-216)"""
+    L = load_library()
+    buf = np.frombuffer(data, np.uint8)
+    st, frame = (C.c_uint32 * 3)(), C.create_string_buffer(256)
+    sp, tn, dist, nn, ne = np.zeros(16), np.zeros(16), C.c_double(), C.c_int64(), C.c_int64()
+    if L.ndtb_graph_msg_unpack(buf.ctypes.data, len(buf), st, frame, 256, sp.ctypes.data, tn.ctypes.data, C.byref(dist), C.byref(nn), None,
+                               None, 0, C.byref(ne), None, None, 0) != 0:
+        raise NdtbError("malformed NDTGraphMsg")
+    no, nl = np.zeros(max(nn.value, 1), np.int64), np.zeros(max(nn.value, 1), np.int64)
+    eo, el = np.zeros(max(ne.value, 1), np.int64), np.zeros(max(ne.value, 1), np.int64)
+    L.ndtb_graph_msg_unpack(buf.ctypes.data, len(buf), st, frame, 256, sp.ctypes.data, tn.ctypes.data, C.byref(dist), C.byref(nn),
+                            no.ctypes.data, nl.ctypes.data, len(no), C.byref(ne), eo.ctypes.data, el.ctypes.data, len(eo))
+    return {"sensor_pose": sp.reshape(4, 4).T.copy(), "Tnow": tn.reshape(4, 4).T.copy(), "distance_moved": dist.value,
+            "nodes": [bytes(data[no[i]: no[i] + nl[i]]) for i in range(nn.value)],
+            "edges": [bytes(data[eo[i]: eo[i] + el[i]]) for i in range(ne.value)], "frame_id": frame.value.decode(), "stamp": tuple(st)}
 
 
 def pose_archive_write(path, T):

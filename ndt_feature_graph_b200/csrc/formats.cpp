@@ -6,6 +6,11 @@
 //   pose archives (*.T)                   saveAffine3d / loadAffine3d used by NDTFeatureNode::save / load,
 //                                         ndt_feature/include/ndt_feature/ndt_feature_node.h:100-152 (boost text archive,
 //                                          byte-compatible with the files in ndt_feature/data/FULL GRAPH/)
+//   ndt_feature/NDTGraphMsg / NDTNodeMsg /  nodeToMsg / fuserHMTToMsg / NDTGraphToMsg and their inverses,
+//   NDTFeatureFuserHMTMsg wire bytes      ndtgraph_conversion.h:36-83,147-216 + ndt_feature/msg/*.msg.  The node message embeds
+//                                         ndt_map/NDTMapMsg of lslgeneric::toMessage [upstream perception_oru, NOT vendored:
+//                                          field order restated from the published ndt_map message definitions — unpinned,
+//                                          no bag in the reference holds such a message]
 //   evaluation trajectory lines           transformToEvalString / transformToEval2dString, ndt_feature/include/ndt_feature/utils.h:243-259
 #include <algorithm>
 #include <cmath>
@@ -134,6 +139,42 @@ bool get_matrix(Reader &r, std::vector<double> &data) {
   return r.ok;
 }
 
+void put_string(Writer &w, const char *s) {
+  const size_t n = s ? std::strlen(s) : 0;
+  w.u32((uint32_t)n);
+  if (n) w.put(s, n);
+}
+bool get_string(Reader &r, std::string &out) {
+  const uint32_t n = r.u32();
+  if (!r.ok || (int64_t)n > r.len - r.at) return r.ok = false;
+  out.assign((const char *)r.p + r.at, n);
+  r.at += n;
+  return true;
+}
+int64_t finish(const Writer &w, uint8_t *out, int64_t cap) {
+  if (out && cap >= (int64_t)w.b.size()) std::memcpy(out, w.b.data(), w.b.size());
+  return (int64_t)w.b.size();
+}
+// skips one NDTEdgeMsg / NDTMapMsg / NDTNodeMsg and reports where it ended
+bool skip_matrix(Reader &r) {
+  std::vector<double> d;
+  return get_matrix(r, d);
+}
+bool skip_map_msg(Reader &r) {
+  std::string f;
+  r.u32(), r.u32(), r.u32();
+  if (!get_string(r, f)) return false;
+  r.at += 9 * 8;
+  const uint32_t n = r.u32();
+  for (uint32_t i = 0; i < n && r.ok; i++) {
+    r.at += 4 * 8;
+    const uint32_t nc = r.u32();
+    r.at += (int64_t)nc * 8 + 8;
+    if (r.at > r.len) r.ok = false;
+  }
+  return r.ok && r.at <= r.len;
+}
+
 std::string g15(double v) {
   char buf[64];
   std::snprintf(buf, sizeof buf, "%.15g", v);
@@ -173,6 +214,175 @@ int ndtb_edge_msg_unpack(const uint8_t *buf, int64_t len, uint32_t *ref_idx, uin
   if (cov36 && c6.size() == 36) std::copy(c6.begin(), c6.end(), cov36);
   if (has_cov36) *has_cov36 = c6.size() == 36;
   if (score) *score = s;
+  return NDTB_OK;
+}
+
+// ---- ndt_map/NDTMapMsg [upstream]: Header, x/y/z_size (metres), x/y/z_cen, x/y/z_cell_size, NDTCellMsg[] cells with
+// NDTCellMsg = mean_x, mean_y, mean_z, occupancy, float64[] cov_matrix (9, row-major), N.  toMessage writes the cells that
+// hold a Gaussian; fromMessage re-inserts every cell at the voxel of its mean (ndtb_map_from_cells with use_idx = 0).
+int64_t ndtb_map_msg_pack(uint32_t seq, uint32_t sec, uint32_t nsec, const char *frame_id, const ndtb_grid *g, const ndtb_cell *cells,
+                          int64_t n_cells, uint8_t *out, int64_t cap) {
+  if (!g || n_cells < 0 || (n_cells > 0 && !cells)) return NDTB_ERR_ARG;
+  Writer w;
+  w.u32(seq), w.u32(sec), w.u32(nsec);
+  put_string(w, frame_id);
+  for (int a = 0; a < 3; a++) w.f64((double)g->size[a] * g->cell[a]);
+  for (int a = 0; a < 3; a++) w.f64(g->center[a]);
+  for (int a = 0; a < 3; a++) w.f64(g->cell[a]);
+  uint32_t ng = 0;
+  for (int64_t i = 0; i < n_cells; i++) ng += cells[i].has_gaussian != 0;
+  w.u32(ng);
+  for (int64_t i = 0; i < n_cells; i++) {
+    const ndtb_cell &c = cells[i];
+    if (!c.has_gaussian) continue;
+    w.f64(c.mean[0]), w.f64(c.mean[1]), w.f64(c.mean[2]);
+    w.f64((double)c.occ);
+    w.u32(9);
+    const double m[9] = {c.cov[0], c.cov[1], c.cov[2], c.cov[1], c.cov[3], c.cov[4], c.cov[2], c.cov[4], c.cov[5]};
+    for (double v : m) w.f64(v);
+    w.f64((double)c.n);
+  }
+  return finish(w, out, cap);
+}
+
+int ndtb_map_msg_unpack(const uint8_t *buf, int64_t len, uint32_t *stamp3, char *frame_id, int32_t frame_cap, ndtb_grid *g,
+                        ndtb_cell *cells, int64_t cells_cap, int64_t *n_cells, int64_t *consumed) {
+  if (!buf || len < 0 || !g) return NDTB_ERR_ARG;
+  Reader r{buf, len};
+  const uint32_t a = r.u32(), b = r.u32(), c = r.u32();
+  std::string frame;
+  if (!get_string(r, frame)) return NDTB_ERR_ARG;
+  double sz[3], cen[3], cs[3];
+  for (double &v : sz) v = r.f64();
+  for (double &v : cen) v = r.f64();
+  for (double &v : cs) v = r.f64();
+  const uint32_t n = r.u32();
+  if (!r.ok) return NDTB_ERR_ARG;
+  for (int q = 0; q < 3; q++) {
+    if (!(cs[q] > 0)) return NDTB_ERR_ARG;
+    g->center[q] = cen[q], g->cell[q] = cs[q];
+    g->size[q] = (int32_t)std::fabs(std::ceil(sz[q] / cs[q]));  // LazyGrid::initialize
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    ndtb_cell cell;
+    std::memset(&cell, 0, sizeof cell);
+    for (double &v : cell.mean) v = r.f64();
+    cell.occ = (float)r.f64();
+    const uint32_t nc = r.u32();
+    if (!r.ok || nc != 9) return NDTB_ERR_ARG;
+    double m[9];
+    for (double &v : m) v = r.f64();
+    cell.cov[0] = m[0], cell.cov[1] = m[1], cell.cov[2] = m[2], cell.cov[3] = m[4], cell.cov[4] = m[5], cell.cov[5] = m[8];
+    cell.n = (int32_t)r.f64();
+    cell.has_gaussian = 1;
+    if (!r.ok) return NDTB_ERR_ARG;
+    if (cells && (int64_t)i < cells_cap) cells[i] = cell;
+  }
+  if (stamp3) stamp3[0] = a, stamp3[1] = b, stamp3[2] = c;
+  if (frame_id && frame_cap > 0) std::snprintf(frame_id, (size_t)frame_cap, "%s", frame.c_str());
+  if (n_cells) *n_cells = n;
+  if (consumed) *consumed = r.at;
+  return NDTB_OK;
+}
+
+// ---- NDTNodeMsg: NDTFeatureFuserHMTMsg map {Pose Tnow, Tlast_fuse, Todom, NDTMapMsg map, u32 ctr}, Pose T,
+// Float64MultiArray cov (3x3), Pose Tlocal_odom, Pose Tlocal_fuse, u32 nbUpdates, f64 time_last_update
+int64_t ndtb_node_msg_pack(const ndtb_node_fields *f, const uint8_t *map_msg, int64_t map_len, uint8_t *out, int64_t cap) {
+  if (!f || !map_msg || map_len <= 0) return NDTB_ERR_ARG;
+  Writer w;
+  put_pose(w, f->Tnow), put_pose(w, f->Tlast_fuse), put_pose(w, f->Todom);
+  w.put(map_msg, (size_t)map_len);
+  w.u32(f->ctr);
+  put_pose(w, f->T);
+  put_matrix(w, f->cov9, 3, 3);
+  put_pose(w, f->Tlocal_odom), put_pose(w, f->Tlocal_fuse);
+  w.u32(f->nb_updates);
+  w.f64(f->time_last_update);
+  return finish(w, out, cap);
+}
+
+int ndtb_node_msg_unpack(const uint8_t *buf, int64_t len, ndtb_node_fields *f, int64_t *map_off, int64_t *map_len, int64_t *consumed) {
+  if (!buf || len < 0 || !f) return NDTB_ERR_ARG;
+  Reader r{buf, len};
+  if (!get_pose(r, f->Tnow) || !get_pose(r, f->Tlast_fuse) || !get_pose(r, f->Todom)) return NDTB_ERR_ARG;
+  const int64_t m0 = r.at;
+  if (!skip_map_msg(r)) return NDTB_ERR_ARG;
+  const int64_t m1 = r.at;
+  f->ctr = r.u32();
+  if (!get_pose(r, f->T)) return NDTB_ERR_ARG;
+  std::vector<double> c3;
+  if (!get_matrix(r, c3) || c3.size() < 9) return NDTB_ERR_ARG;  // msgToNode reads nine values
+  std::copy(c3.begin(), c3.begin() + 9, f->cov9);
+  if (!get_pose(r, f->Tlocal_odom) || !get_pose(r, f->Tlocal_fuse)) return NDTB_ERR_ARG;
+  f->nb_updates = r.u32();
+  f->time_last_update = r.f64();
+  if (!r.ok) return NDTB_ERR_ARG;
+  if (map_off) *map_off = m0;
+  if (map_len) *map_len = m1 - m0;
+  if (consumed) *consumed = r.at;
+  return NDTB_OK;
+}
+
+// ---- NDTGraphMsg: Header, Pose sensor_pose_, Pose Tnow, f64 distance_moved_in_last_node_, NDTNodeMsg[] nodes, NDTEdgeMsg[] edges
+int64_t ndtb_graph_msg_pack(uint32_t seq, uint32_t sec, uint32_t nsec, const char *frame_id, const double *sensor_pose16,
+                            const double *Tnow16, double distance_moved, int64_t n_nodes, const uint8_t *const *node_msgs,
+                            const int64_t *node_lens, int64_t n_edges, const uint8_t *const *edge_msgs, const int64_t *edge_lens,
+                            uint8_t *out, int64_t cap) {
+  if (!sensor_pose16 || !Tnow16 || n_nodes < 0 || n_edges < 0 || (n_nodes > 0 && (!node_msgs || !node_lens)) ||
+      (n_edges > 0 && (!edge_msgs || !edge_lens)))
+    return NDTB_ERR_ARG;
+  Writer w;
+  w.u32(seq), w.u32(sec), w.u32(nsec);
+  put_string(w, frame_id);
+  put_pose(w, sensor_pose16), put_pose(w, Tnow16);
+  w.f64(distance_moved);
+  w.u32((uint32_t)n_nodes);
+  for (int64_t i = 0; i < n_nodes; i++) w.put(node_msgs[i], (size_t)node_lens[i]);
+  w.u32((uint32_t)n_edges);
+  for (int64_t i = 0; i < n_edges; i++) w.put(edge_msgs[i], (size_t)edge_lens[i]);
+  return finish(w, out, cap);
+}
+
+int ndtb_graph_msg_unpack(const uint8_t *buf, int64_t len, uint32_t *stamp3, char *frame_id, int32_t frame_cap, double *sensor_pose16,
+                          double *Tnow16, double *distance_moved, int64_t *n_nodes, int64_t *node_off, int64_t *node_len,
+                          int64_t nodes_cap, int64_t *n_edges, int64_t *edge_off, int64_t *edge_len, int64_t edges_cap) {
+  if (!buf || len < 0) return NDTB_ERR_ARG;
+  Reader r{buf, len};
+  const uint32_t a = r.u32(), b = r.u32(), c = r.u32();
+  std::string frame;
+  if (!get_string(r, frame)) return NDTB_ERR_ARG;
+  double sp[16], tn[16];
+  if (!get_pose(r, sp) || !get_pose(r, tn)) return NDTB_ERR_ARG;
+  const double dist = r.f64();
+  const uint32_t nn = r.u32();
+  if (!r.ok) return NDTB_ERR_ARG;
+  for (uint32_t i = 0; i < nn; i++) {
+    ndtb_node_fields f;
+    int64_t used = 0;
+    if (ndtb_node_msg_unpack(buf + r.at, len - r.at, &f, nullptr, nullptr, &used) != NDTB_OK) return NDTB_ERR_ARG;
+    if (node_off && (int64_t)i < nodes_cap) node_off[i] = r.at;
+    if (node_len && (int64_t)i < nodes_cap) node_len[i] = used;
+    r.at += used;
+  }
+  const uint32_t ne = r.u32();
+  if (!r.ok) return NDTB_ERR_ARG;
+  for (uint32_t i = 0; i < ne; i++) {
+    const int64_t e0 = r.at;
+    r.u32(), r.u32();
+    double T[16];
+    if (!get_pose(r, T) || !skip_matrix(r) || !skip_matrix(r)) return NDTB_ERR_ARG;
+    r.f64();
+    if (!r.ok) return NDTB_ERR_ARG;
+    if (edge_off && (int64_t)i < edges_cap) edge_off[i] = e0;
+    if (edge_len && (int64_t)i < edges_cap) edge_len[i] = r.at - e0;
+  }
+  if (stamp3) stamp3[0] = a, stamp3[1] = b, stamp3[2] = c;
+  if (frame_id && frame_cap > 0) std::snprintf(frame_id, (size_t)frame_cap, "%s", frame.c_str());
+  if (sensor_pose16) std::copy(sp, sp + 16, sensor_pose16);
+  if (Tnow16) std::copy(tn, tn + 16, Tnow16);
+  if (distance_moved) *distance_moved = dist;
+  if (n_nodes) *n_nodes = nn;
+  if (n_edges) *n_edges = ne;
   return NDTB_OK;
 }
 

@@ -193,3 +193,28 @@ def test_graph_replay_matches_oracle_and_the_shipped_maps(golden, engine, F):
         lin = FC.lin_index(cells)
         mine, ref = set(lin[cells["has_gaussian"] == 1].tolist()), set(golden[f"gidx{k}"].tolist())
         assert len(mine & ref) / len(mine | ref) > 0.8
+    # hand-off: the graph as ndt_feature/NDTGraphMsg bytes (NDTGraphToMsg) and back (msgToNDTGraph): every node map that
+    # comes out of the message holds the Gaussian cells of the resident map, at the same voxels
+    from ndt_feature_graph_b200 import api
+    import ndt_feature_graph_b200 as N
+
+    node_msgs = []
+    for b in nodes:
+        cen, cs, sz = b.map.map.grid()
+        g = api.Grid((api.C.c_double * 3)(*cen), (api.C.c_double * 3)(*cs), (api.C.c_int32 * 3)(*[int(s) for s in sz]))
+        f = api.NodeFields.make(T=b.T, Tlocal_odom=b.Tlocal_odom, Tlocal_fuse=b.Tlocal_fuse, Tnow=b.Tlocal_fuse, nb_updates=b.nbUpdates)
+        node_msgs.append(api.node_msg_pack(f, api.map_msg_pack(g, b.map.map.export_cells(False))))
+    edge_msgs = [api.edge_msg_pack(k, k + 1, nodes[k].Tlocal_fuse, np.eye(3), None, 0.0) for k in range(7)]
+    msg = api.graph_msg_pack(FC.SENSOR, Tg, 0.0, node_msgs, edge_msgs)
+    back = api.graph_msg_unpack(msg)
+    assert len(back["nodes"]) == 8 and len(back["edges"]) == 7 and np.abs(back["Tnow"] - Tg).max() < 1e-9
+    for b, nm in zip(nodes, back["nodes"]):
+        f, mm, _ = api.node_msg_unpack(nm)
+        assert np.abs(f.pose("T") - b.T).max() < 1e-9 and f.nb_updates == b.nbUpdates
+        g, cells, frame, _, _ = api.map_msg_unpack(mm)
+        m2 = N.NDTMap(engine, float(g.cell[0])).from_cells(list(g.center), list(g.cell), list(g.size), cells, use_idx=False)
+        a0, a1 = b.map.map.export_cells(True), m2.export_cells(True)
+        assert len(a0) == len(a1) > 20
+        o0, o1 = np.argsort(FC.lin_index(a0)), np.argsort(FC.lin_index(a1))
+        for fld in ("idx", "mean", "cov", "n"):
+            assert np.array_equal(a0[fld][o0], a1[fld][o1]), fld

@@ -801,7 +801,10 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
     gt_total += (size_t)std::max(tgt[e]->ng, 1);
   }
   const MatchConfig cfg = make_config(ctx, p, max_tsize);
-  const int n_chunks = 8;
+  // CTAs per registration in the covariance pass: a small batch wants them all for latency, a large one fewer and longer
+  // ones (12 warps share the rounds of a chunk: 2-3 rounds per warp leave a third of them idle at the end)
+  static const int env_chunks = std::getenv("NDTB_COV_CHUNKS") ? std::atoi(std::getenv("NDTB_COV_CHUNKS")) : 0;
+  const int n_chunks = env_chunks > 0 ? env_chunks : (n >= 2 * ctx->sm_count ? 3 : 8);
   Carver c;
   const size_t o_jobs = c.take(sizeof(MatchJob) * n), o_res = c.take(sizeof(ndtb_result) * n);
   const size_t o_goff = c.take(8 * n), o_gt = c.take(with_cov ? 48 * gt_total : 0);

@@ -64,13 +64,17 @@ struct SmemAcc {
 // it).  Pairs are spread over the lanes, so both kinds of rows are summed with 64-bit FIXED-POINT atomics (2^-36
 // resolution): integer addition is associative, the result does not depend on the order the pairs arrive in.
 constexpr double COV_FIX = 68719476736.0;  // 2^36
-constexpr int COV2_THREADS = 256;
+#ifndef NDTB_COV_THREADS
+#define NDTB_COV_THREADS 384  // B200 A/B per 592 C2 pairs: 256 thr (227 regs) 5.38 ms, 384 thr (168 regs) 4.37 ms, 512 thr (128 regs, spills) 4.64 ms
+#endif
+constexpr int COV2_THREADS = NDTB_COV_THREADS;
 struct CovAcc {
   static constexpr bool kPairHook = true;
-  double *slot;               // Hessian sums: per-lane shared-memory slots, stride COV2_THREADS
+  double *acc;                // Hessian sums (21 updates per pair): the thread's registers, like RegAcc
+  double *gg;                 // sum g g^T over the source rows (21 updates per SOURCE CELL): per-lane shared-memory slots
   unsigned long long *gs;     // [32][6] source rows of the warp's current round (shared)
   unsigned long long *gt;     // [n target cells][6] target rows of this registration (global)
-  __device__ __forceinline__ void add(int i, double v) const { slot[i * COV2_THREADS] += v; }
+  __device__ __forceinline__ void add(int i, double v) const { acc[ACC_H + i] += v; }
   __device__ __forceinline__ void pair(int src_lane, int tgt_slot, const double *g6) const {
 #pragma unroll
     for (int a = 0; a < 6; a++) {
@@ -357,7 +361,7 @@ __device__ void d2d_pass(const PassCtx &c, const double *P, WarpScratch &ws, int
 #pragma unroll
       for (int a = 0; a < 6; a++)
 #pragma unroll
-        for (int b = a; b < 6; b++) acc[ACC_TOTAL + n++] += g[a] * g[b];
+        for (int b = a; b < 6; b++) ha.gg[(n++) * COV2_THREADS] += g[a] * g[b];
       __syncwarp();
     }
   }
@@ -721,22 +725,22 @@ cov_pass_kernel(const MatchJob *__restrict__ jobs, MatchConfig cfg, const ndtb_r
   for (int j = 0; j < 21; j++) hs[j * COV2_THREADS + threadIdx.x] = 0.0;
   for (int a = 0; a < 6; a++) gs_all[(warp * 32 + lane) * 6 + a] = 0ull;
   __syncthreads();
-  double acc[ACC_TOTAL + 21];  // [0] score, [1..6] g, [28] pairs, [29..49] upper triangle of sum g g^T over source rows
+  double acc[ACC_TOTAL];  // [0] score, [1..6] g, [7..27] H, [28] pairs; sum g g^T over the source rows: shared slots hs
 #pragma unroll
-  for (int j = 0; j < ACC_TOTAL + 21; j++) acc[j] = 0.0;
+  for (int j = 0; j < ACC_TOTAL; j++) acc[j] = 0.0;
   if (!skip) {
     PassCtx c;
     c.g = &sh.grid;
     c.table = job.tgt.table, c.tsize = job.tgt.tsize, c.tcell = job.tgt.gcell;
     c.scell = job.src_gcell, c.ns = job.src_ng;
     c.k = cfg.n_neighbours, c.lfd1 = cfg.lfd1, c.lfd2 = cfg.lfd2;
-    const CovAcc ha{hs + threadIdx.x, gs_all + warp * 32 * 6, reinterpret_cast<unsigned long long *>(gt + gt_off[blockIdx.x] * 6)};
+    const CovAcc ha{acc, hs + threadIdx.x, gs_all + warp * 32 * 6, reinterpret_cast<unsigned long long *>(gt + gt_off[blockIdx.x] * 6)};
     d2d_pass<true, CovAcc>(c, sh.P, wsp[warp], blockIdx.y * NW + warp, gridDim.y * NW, acc, ha);
   }
   // block reduce the 49 values (fixed tree) -> partial[job][chunk][COV_W]: [0..6] score+g, [7..27] H, [28..48] sum g g^T
 #pragma unroll
   for (int j = 0; j < 49; j++) {
-    double v = j < 7 ? acc[j] : (j < 28 ? hs[(j - 7) * COV2_THREADS + threadIdx.x] : acc[ACC_TOTAL + (j - 28)]);
+    double v = j < 28 ? acc[j] : hs[(j - 28) * COV2_THREADS + threadIdx.x];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
     if (lane == 0) sh.red[warp * 49 + j] = v;

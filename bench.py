@@ -497,6 +497,37 @@ def run_gpu(args):
     B = args.pairs
     # every rank owns B distinct pairs of one workload (weak scaling: per-GPU work fixed): pairs [rank*B, (rank+1)*B)
     tg, sr, T0s, Ds = synth.velodyne_batch(B, n_base=args.base, seed=0, start=rank * B)
+    shard_note = "pairs [rank*B, (rank+1)*B) of one workload"
+    if world > 1 and not args.no_balance:
+        # Cost-balanced shards (sharding.balance_by_cost's idea with equal counts): the step time is the MAX over ranks, and
+        # a rank that drew 17 registrations that run into ITR_MAX (200-340 derivative passes each) instead of 6 has 6 % more
+        # work.  One untimed run on the natural shards measures every pair's passes; the world*B pairs are then dealt in
+        # descending cost, boustrophedon over the ranks, so every rank owns B pairs of (nearly) the same total cost.  Pairs
+        # are a function of their global index: a rank regenerates the ones it did not own.
+        e0 = N.Engine(local)
+        r0, _ = e0.register_scans(tg, sr, T0s, cell=CELL, with_covariance=False)
+        del e0
+        cost = torch.tensor(np.asarray(r0["n_exec_passes"], dtype=np.int64), device=dev)
+        allc = [torch.zeros_like(cost) for _ in range(world)]
+        dist.all_gather(allc, cost)
+        gcost = torch.cat(allc).cpu().numpy()
+        order = np.argsort(-gcost, kind="stable")
+        owner = np.empty(world * B, np.int64)
+        for jpos, g in enumerate(order):
+            q, r = divmod(jpos, world)
+            owner[g] = r if q % 2 == 0 else world - 1 - r
+        mine = np.flatnonzero(owner == rank)
+        assert len(mine) == B
+        have = {rank * B + i: i for i in range(B)}
+        need = [int(g) for g in mine if int(g) not in have]
+        ntg, nsr, nT0, nD = synth.velodyne_batch(0, n_base=args.base, seed=0, indices=need) if need else ([], [], [], [])
+        got = {g: i for i, g in enumerate(need)}
+        tg = [tg[have[g]] if g in have else ntg[got[g]] for g in map(int, mine)]
+        sr = [sr[have[g]] if g in have else nsr[got[g]] for g in map(int, mine)]
+        T0s = [T0s[have[g]] if g in have else nT0[got[g]] for g in map(int, mine)]
+        Ds = [Ds[have[g]] if g in have else nD[got[g]] for g in map(int, mine)]
+        shard_note = f"world*B pairs of one workload dealt by measured cost (passes of an untimed run): rank {rank} keeps {B - len(need)} of its own"
+        del ntg, nsr, r0
     # `lanes` contexts (one host thread + one stream each, the ABI's "one ndtb_ctx per host thread") take the steps in turn:
     # while one step's last registrations (the few that need hundreds of passes) finish on a few SMs, the next step's
     # kernels fill the rest of the GPU.  Every step does the full work on the same B pairs.
@@ -722,7 +753,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "base_scenes": args.base, "lanes": lanes_d,
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "shards": shard_note, "base_scenes": args.base, "lanes": lanes_d,
                        "points_per_scan": int(np.mean([c.shape[0] for c in tg])),
                        "gaussian_cells_per_map": int(res["n_tgt_cells"].mean()),
                        "n_neighbours": int(prm.n_neighbours), "delta_score": prm.delta_score,
@@ -815,6 +846,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) leg: profiling runs only")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (c4, c5): profiling runs only")
+    ap.add_argument("--no-balance", action="store_true", help="multi-GPU: keep the natural index ranges instead of cost-balanced shards")
     ap.add_argument("--lanes", type=int, default=3, help="contexts (host thread + stream each) the device-resident leg alternates its steps between")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="contexts (host threads) the e2e leg alternates its steps between")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the step timed on the CPU (0 = auto, ~10-30 s)")

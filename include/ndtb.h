@@ -28,7 +28,9 @@
  *     the ABI, nothing blocks on stdin (cf. ndt_feature_graph.cpp:318-328), nothing prints.
  *   - a ndtb_ctx is single-owner (one per host thread / per GPU); calls are synchronous at return
  *     unless every output lives in device memory (NDTB_MEM_DEVICE), in which case work is only
- *     enqueued on the context's stream.
+ *     enqueued on the context's stream.  Maps are used with the context that created them: a matcher /
+ *     overlap call with a map of another context returns NDTB_ERR_ARG (map storage is recycled in the
+ *     order of its own context's stream).
  *   - there is NO CPU implementation behind this ABI: without a CUDA device every compute entry
  *     point fails with NDTB_ERR_CUDA.
  */

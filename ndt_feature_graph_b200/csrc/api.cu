@@ -793,6 +793,7 @@ int match_batch_impl(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *tgt, const
   std::vector<long long> gt_off((size_t)n);
   for (int64_t e = 0; e < n; e++) {
     if (!map_ok(tgt[e]) || !map_ok(src[e])) return NDTB_ERR_GRID;
+    if (tgt[e]->ctx != ctx || src[e]->ctx != ctx) return NDTB_ERR_ARG;  // storage is released in the order of its own context's stream
     if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(tgt[e]))) return rc;
     if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(src[e]))) return rc;
     fill_job(jobs[e], tgt[e], src[e], T0s + 16 * e, Q36s ? Q36s + 36 * e : nullptr);
@@ -1489,6 +1490,7 @@ int ndtb_d2d_derivatives(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src
   DeviceGuard dev_guard(ctx);
   if (!ctx || !tgt || !src || !T || !p || !out43) return NDTB_ERR_ARG;
   if (!map_ok(tgt) || !map_ok(src)) return NDTB_ERR_GRID;
+  if (tgt->ctx != ctx || src->ctx != ctx) return NDTB_ERR_ARG;  // storage is released in the order of its own context's stream
   if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(tgt))) return rc;
   if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(src))) return rc;
   MatchJob j;
@@ -1632,6 +1634,7 @@ int ndtb_d2d_covariance(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src,
   DeviceGuard dev_guard(ctx);
   if (!ctx || !tgt || !src || !T || !p || !cov36) return NDTB_ERR_ARG;
   if (!map_ok(tgt) || !map_ok(src)) return NDTB_ERR_GRID;
+  if (tgt->ctx != ctx || src->ctx != ctx) return NDTB_ERR_ARG;  // storage is released in the order of its own context's stream
   if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(tgt))) return rc;
   if (int rc = ensure_view(ctx, const_cast<ndtb_map *>(src))) return rc;
   cudaStream_t st = ctx->stream;
@@ -1801,6 +1804,7 @@ int ndtb_overlap_score_batch(ndtb_ctx *ctx, int64_t n, const ndtb_map *const *re
     const ndtb_map *mm[2] = {ref[l], mov[l]};
     for (int i = 0; i < 2; i++) {
       if (!map_ok(mm[i])) return NDTB_ERR_GRID;
+      if (mm[i]->ctx != ctx) return NDTB_ERR_ARG;
       BuildJob &b = j[(size_t)(2 * l + i)];
       b.g = mm[i]->g;
       mm[i]->fill_box(b);

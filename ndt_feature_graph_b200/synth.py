@@ -226,14 +226,15 @@ def _apply(G, cloud):
     return out
 
 
-def velodyne_batch(n_pairs, n_base=8, seed=0, n_rings=64, n_az=1563, start=0):
-    """Pairs [start, start + n_pairs) of the C2 workload `seed`.  n_base scenes are ray-cast (slow, numpy); pair i is base
+def velodyne_batch(n_pairs, n_base=8, seed=0, n_rings=64, n_az=1563, start=0, indices=None):
+    """Pairs [start, start + n_pairs) — or the pairs `indices` — of the C2 workload `seed`.  n_base scenes are ray-cast (slow, numpy); pair i is base
     pair i % n_base moved by its own rigid transform G_i (both scans), which changes the voxelisation of both maps, so
     all pairs are distinct data.  G_i and the initial guess depend only on (seed, i): ranks of a multi-GPU run take
     disjoint index ranges of ONE workload.  Returns lists (target clouds, source clouds, initial guesses T0, true D)."""
-    base = [velodyne_pair(100 * seed + b, n_rings, n_az) for b in range(min(n_base, start + n_pairs))]
+    idx = list(range(start, start + n_pairs)) if indices is None else [int(i) for i in indices]
+    base = [velodyne_pair(100 * seed + b, n_rings, n_az) for b in range(min(n_base, (max(idx) + 1) if idx else 0))]
     tg, sr, T0s, Ds = [], [], [], []
-    for i in range(start, start + n_pairs):
+    for i in idx:
         ca, cb, D = base[i % len(base)]
         if i < len(base):
             G = np.eye(4)

@@ -537,3 +537,17 @@ def test_overlap_scores_batched(engine, oracle, gpu_fixture_maps, oracle_fixture
     got = engine.overlap_scores(gpu_fixture_maps[:7], gpu_fixture_maps[1:8], Ts)
     for k in range(7):
         assert abs(got[k] - oracle.overlap_occupancy_score(oracle_fixture_maps[k], oracle_fixture_maps[k + 1], Ts[k])) < 1e-12
+
+
+def test_maps_of_another_context_are_rejected(engine):
+    """map storage is recycled in the stream order of the context that owns it: a match across contexts is an argument error"""
+    import ndt_feature_graph_b200 as N
+    from ndt_feature_graph_b200 import api
+
+    other = N.Engine(0)
+    ca, cb, D = synth.corridor_pair(3) if hasattr(synth, "corridor_pair") else synth.velodyne_pair(3)
+    a, b = N.NDTMap(engine, 0.5), N.NDTMap(other, 0.5)
+    engine.build_maps([a], [ca])
+    other.build_maps([b], [cb])
+    with pytest.raises(api.NdtbError):
+        engine.match_batch([a], [b], [np.eye(4)])

@@ -485,6 +485,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # result records are tiny: one CTA per collective (NCCL kernels spin on their SMs while they wait for the slowest rank)
+        os.environ.setdefault("NCCL_MAX_CTAS", "1")
         dist.init_process_group("nccl", device_id=dev)
         # every rank keeps to its own share of the host cores (its lanes' host threads, pinned buffers' first touch)
         try:

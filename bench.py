@@ -513,11 +513,7 @@ def run_gpu(args):
         allc = [torch.zeros_like(cost) for _ in range(world)]
         dist.all_gather(allc, cost)
         gcost = torch.cat(allc).cpu().numpy()
-        order = np.argsort(-gcost, kind="stable")
-        owner = np.empty(world * B, np.int64)
-        for jpos, g in enumerate(order):
-            q, r = divmod(jpos, world)
-            owner[g] = r if q % 2 == 0 else world - 1 - r
+        owner = sharding.deal_by_cost(gcost, world)
         mine = np.flatnonzero(owner == rank)
         assert len(mine) == B
         have = {rank * B + i: i for i in range(B)}

@@ -32,6 +32,23 @@ def balance_by_cost(costs, world):
     return [np.array(sorted(o), dtype=np.int64) for o in owner]
 
 
+def deal_by_cost(costs, world):
+    """Equal-COUNT shards of equal total cost: items in descending cost, dealt boustrophedon over the ranks (0..w-1, w-1..0,
+    ...).  len(costs) must be a multiple of world.  Returns owner[i] = rank of item i.  bench.py deals the world x B scan
+    pairs of a multi-GPU run this way from the derivative passes of an untimed run: the step time is the MAX over ranks,
+    and a rank that drew more registrations that run into ITR_MAX would set it."""
+    costs = np.asarray(costs)
+    n = costs.shape[0]
+    if n % world:
+        raise ValueError("deal_by_cost: item count must be a multiple of the world size")
+    order = np.argsort(-costs, kind="stable")
+    pos = np.arange(n)
+    q, r = pos // world, pos % world
+    owner = np.empty(n, np.int64)
+    owner[order] = np.where(q % 2 == 0, r, world - 1 - r)
+    return owner
+
+
 def gather_results(local_records, n_total, rank, world, device=None):
     """All-gather of per-edge result records.  `local_records`: structured numpy array (api.RESULT_DTYPE) or a uint8
     torch tensor already on `device`, holding this rank's shard_range block.  Returns the n_total records in edge order

@@ -29,6 +29,37 @@ def test_balance_by_cost():
     assert loads.max() - loads.min() <= costs.max()
 
 
+def test_deal_by_cost_equal_counts_and_balanced_sums():
+    """the multi-GPU bench deals world x B scan pairs by measured passes: equal counts, sums within one item's spread"""
+    rng = np.random.default_rng(1)
+    for world in (2, 4, 8):
+        B = 592
+        # the C2 distribution: most registrations take 20-60 passes, ~2 % run into ITR_MAX with 200-340
+        costs = rng.integers(20, 60, size=world * B)
+        slow = rng.choice(world * B, size=int(0.02 * world * B), replace=False)
+        costs[slow] = rng.integers(200, 340, size=slow.size)
+        owner = sharding.deal_by_cost(costs, world)
+        assert np.array_equal(np.bincount(owner, minlength=world), np.full(world, B))
+        loads = np.array([costs[owner == r].sum() for r in range(world)])
+        natural = np.array([costs[r * B:(r + 1) * B].sum() for r in range(world)])
+        assert loads.max() - loads.min() <= 340 and loads.max() - loads.min() <= natural.max() - natural.min()
+        heavy = np.array([(costs[owner == r] >= 200).sum() for r in range(world)])
+        assert heavy.max() - heavy.min() <= 1
+        assert np.array_equal(owner, sharding.deal_by_cost(costs, world))  # deterministic: every rank computes the same deal
+    with pytest.raises(ValueError):
+        sharding.deal_by_cost(np.ones(7), 2)
+
+
+def test_workload_pairs_are_a_function_of_their_index():
+    """a rank regenerates the pairs it is dealt: velodyne_batch(indices=...) returns the pairs of the contiguous call"""
+    from ndt_feature_graph_b200 import synth
+
+    a = synth.velodyne_batch(3, n_base=2, seed=0, start=4, n_rings=8, n_az=100)
+    b = synth.velodyne_batch(0, n_base=2, seed=0, indices=[6, 4], n_rings=8, n_az=100)
+    assert np.array_equal(a[0][2], b[0][0]) and np.array_equal(a[1][2], b[1][0]) and np.array_equal(a[2][2], b[2][0])
+    assert np.array_equal(a[0][0], b[0][1]) and np.array_equal(a[3][0], b[3][1])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

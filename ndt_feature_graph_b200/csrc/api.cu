@@ -1280,7 +1280,8 @@ int ndtb_map_build_batch(ndtb_ctx *ctx, int64_t n_maps, ndtb_map *const *maps, c
   if (int rc = slab_alloc(ctx, c.off, big)) return rc;
   for (int64_t i = 0; i < n_maps; i++) ps[i] = {(const float4 *)(big->p + off[i]), (int)n_pts[i]};
   int n_chunks = 1;
-  if (n_maps >= 16 && total >= ((size_t)32 << 20)) n_chunks = (int)std::min<int64_t>(8, n_maps / 8);
+  static const int env_h2d_chunks = std::getenv("NDTB_H2D_CHUNKS") ? std::atoi(std::getenv("NDTB_H2D_CHUNKS")) : 0;
+  if (n_maps >= 16 && total >= ((size_t)32 << 20)) n_chunks = (int)std::min<int64_t>(env_h2d_chunks > 0 ? env_h2d_chunks : (n_maps >= 512 ? 4 : 8), n_maps / 8);  // B200, 1184 maps, 3 lanes: 2 chunks 9.06 k, 4: 9.33 k, 8: 9.15 k, 16: 8.46 k reg/s
   if (n_chunks > 1 && !ctx->copy_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   while ((int)ctx->copy_events.size() < n_chunks + 1) {
     cudaEvent_t e;

@@ -626,7 +626,8 @@ __global__ void k_cell_keys(const BuildJob *__restrict__ jobs) {
 // max_sweeps < 64: *deferred is set (and cov left untouched) when the Jacobi iteration needs more sweeps than that
 __device__ bool rescale_covariance(double *cov, int max_sweeps = 64, bool *deferred = nullptr) {
   double ev[3], V[9];
-  const bool done = eig_sym_n<3>(cov, ev, V, max_sweeps);
+  // the deferred cells (second pass, full sweep cap) stop at the fixed point of the iteration: see eig_sym_n
+  const bool done = deferred ? eig_sym_n<3, false>(cov, ev, V, max_sweeps) : eig_sym_n<3, true>(cov, ev, V, max_sweeps);
   if (deferred) *deferred = !done;
   if (!done) return false;
   if (ev[0] <= 0 || ev[1] <= 0 || ev[2] <= 0) return false;
@@ -862,8 +863,11 @@ __global__ void __launch_bounds__(128, NDTB_KCELLS_MINBLOCKS) k_cells(const Buil
 // so the first pass stops after EIG_FAST_SWEEPS and defers those cells to a compact second list (the dead `cell_key`
 // array) that k_eigen_hard works through with full warps.  Same operations per cell either way: bit-identical results.
 constexpr int EIG_FAST_SWEEPS = 8;
+#ifndef NDTB_EIGEN_MINBLOCKS
+#define NDTB_EIGEN_MINBLOCKS 6  // B200 A/B of k_eigen: 6 (80 registers) 1.19 ms, 5 (96) 1.29 ms, 4 (114, no spills) 1.46 ms
+#endif
 
-__global__ void __launch_bounds__(128, 6) k_eigen(const BuildJob *__restrict__ jobs) {
+__global__ void __launch_bounds__(128, NDTB_EIGEN_MINBLOCKS) k_eigen(const BuildJob *__restrict__ jobs) {
   const BuildJob &j = jobs[blockIdx.y];
   const int n = j.counts[5];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
@@ -883,7 +887,7 @@ __global__ void __launch_bounds__(128, 6) k_eigen(const BuildJob *__restrict__ j
   }
 }
 
-__global__ void __launch_bounds__(128, 6) k_eigen_hard(const BuildJob *__restrict__ jobs) {
+__global__ void __launch_bounds__(128, 4) k_eigen_hard(const BuildJob *__restrict__ jobs) {
   const BuildJob &j = jobs[blockIdx.y];
   const int n = j.counts[6];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {

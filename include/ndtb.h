@@ -206,6 +206,11 @@ int ndtb_d2d_line_search_cells(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_ce
 /* NDTMatcherD2D::MoreThuente::cstep [upstream] == MINPACK dcstep (ndt_matcher_d2d_fusion.h:347,366,756,775): returns info */
 int ndtb_mt_cstep(double *stx, double *fx, double *dx, double *sty, double *fy, double *dy, double *stp, double fp, double dp,
                   int *brackt, double stmin, double stmax);
+/* Host hook of the engine's 3x3 symmetric eigen-solver (cyclic Jacobi: the decomposition behind NDTCell::rescaleCovariance in
+ * the map build; csrc/optimizer.h eig_sym_n<3>).  stop_at_fixed_point = 1 is what the build runs on the covariances that
+ * never meet the stopping test: it returns when a sweep changes no bit — the CPU tests check that this is bit-identical to
+ * the full 64 sweeps.  A9 row-major; evals ascending; V9 eigenvectors in columns; sweeps (optional) = sweeps actually run. */
+int ndtb_eig_sym3(const double *A9, int stop_at_fixed_point, double *evals3, double *V9, int32_t *sweeps);
 int ndtb_d2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0,
                    const ndtb_params *p, ndtb_result *res);
 /* matchFusion with useNDT=true, useFeat=false: soft constraint Q = Tcov^-1 (Tcov36 row-major 6x6) */

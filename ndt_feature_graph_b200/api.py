@@ -159,6 +159,7 @@ def load_library():
         "ndtb_d2d_derivatives_cells": (C.c_int, [vp, vp, vp, i64, vp, PP, C.c_int, vp, C.POINTER(i64)]),
         "ndtb_d2d_line_search_cells": (C.c_int, [vp, vp, vp, i64, vp, PP, C.POINTER(dbl)]),
         "ndtb_mt_cstep": (C.c_int, [C.POINTER(dbl)] * 7 + [dbl, dbl, C.POINTER(C.c_int), dbl, dbl]),
+        "ndtb_eig_sym3": (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(C.c_int32)]),
         "ndtb_map_load_point_cloud_centroid": (C.c_int, [vp, vp, i64, C.c_int, vp, vp, vp, dbl]),
         "ndtb_overlap_score_batch": (C.c_int, [vp, i64, vp, vp, vp, i64, C.c_int, C.c_int, vp]),
         "ndtb_edge_msg_pack": (i64, [C.c_uint32, C.c_uint32, vp, vp, vp, dbl, vp, i64]),

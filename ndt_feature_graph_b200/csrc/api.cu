@@ -1606,6 +1606,14 @@ int ndtb_mt_cstep(double *stx, double *fx, double *dx, double *sty, double *fy, 
   return info;
 }
 
+int ndtb_eig_sym3(const double *A9, int stop_at_fixed_point, double *evals3, double *V9, int32_t *sweeps) {
+  if (!A9 || !evals3 || !V9) return NDTB_ERR_ARG;
+  int n = 0;
+  const bool ok = stop_at_fixed_point ? eig_sym_n<3, true>(A9, evals3, V9, 64, &n) : eig_sym_n<3, false>(A9, evals3, V9, 64, &n);
+  if (sweeps) *sweeps = n;
+  return ok ? 1 : 0;
+}
+
 int ndtb_d2d_match(ndtb_ctx *ctx, const ndtb_map *tgt, const ndtb_map *src, const double *T0, const ndtb_params *p,
                    ndtb_result *res) {
   DeviceGuard dev_guard(ctx);

@@ -145,13 +145,14 @@ NDTB_HDF inline bool same_bits(double a, double b) {
 // TRACK is a template flag because the bookkeeping costs the cells that converge in 2-4 sweeps more than it saves them (B200:
 // k_eigen 1.01 -> 1.19 ms with it, k_eigen_hard 0.48 -> 0.11 ms): the map build turns it on for the deferred cells only.
 template <int n, bool TRACK = false>
-NDTB_HDF inline bool eig_sym_n(const double *Ain, double *evals, double *V, int max_sweeps = 64) {
+NDTB_HDF inline bool eig_sym_n(const double *Ain, double *evals, double *V, int max_sweeps = 64, int *sweeps_run = nullptr) {
   double A[n * n];
   for (int i = 0; i < n * n; i++) A[i] = Ain[i];
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
   bool converged = max_sweeps >= 64;
-  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+  int sweep = 0;
+  for (; sweep < max_sweeps; sweep++) {
     double off = 0, diag = 0;
     for (int i = 0; i < n; i++)
       for (int j = 0; j < n; j++) {
@@ -197,9 +198,11 @@ NDTB_HDF inline bool eig_sym_n(const double *Ain, double *evals, double *V, int 
       }
     if (!changed) {  // fixed point: the remaining sweeps would repeat this one
       converged = true;
+      sweep++;
       break;
     }
   }
+  if (sweeps_run) *sweeps_run = sweep;
   // stable ascending order by eigenvalue (selection network free of dynamic indexing for small n)
   double d[n];
   int order[n];

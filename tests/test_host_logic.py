@@ -184,3 +184,47 @@ def test_abi_cstep_matches_oracle(oracle):
         info_g = L.ndtb_mt_cstep(*[C.byref(x) for x in v], fp, dp, C.byref(b), min(stx, sty), max(stx, sty) + 1.0)
         assert info_g == info_o and bool(b.value) == b_o
         assert all((a.value == o) or (np.isnan(a.value) and np.isnan(o)) for a, o in zip(v, vals_o))
+
+
+def test_eigen_fixed_point_stop_is_bit_identical_to_64_sweeps(oracle):
+    """The map build lets the exactly singular covariances (collinear / 3-point cells) stop at the bitwise fixed point of the
+    Jacobi iteration instead of running all 64 sweeps.  On the CPU, through the C ABI hook: eigenvalues and eigenvectors are
+    bit-identical to the full iteration and to the oracle's own solver, on degenerate and on ordinary covariances."""
+    import ctypes as C
+
+    import numpy as np
+
+    from ndt_feature_graph_b200 import api
+
+    L = api.load_library()
+    rng = np.random.default_rng(7)
+    n_never, max_fixed = 0, 0
+    for trial in range(6000):
+        npts = 3 + trial % 3
+        c = rng.uniform(-0.25, 0.25, 3) + np.array([10.0, -7.0, 1.0])
+        d = rng.uniform(-0.25, 0.25, 3) * np.array([1.0, 1.0, 0.1])
+        t = rng.uniform(-0.5, 0.5, (npts, 1))
+        P = c + t * d  # collinear points ...
+        if trial % 2 == 0:
+            P[0] += rng.uniform(-0.05, 0.05, 3)  # ... or coplanar ones
+        if trial % 7 == 0:
+            P = c + rng.uniform(-0.25, 0.25, (npts + 5, 3))  # an ordinary cell
+        P = P.astype(np.float32).astype(np.float64)
+        m = P.mean(0)
+        A = np.ascontiguousarray((P - m).T @ (P - m) / (len(P) - 1))
+        out = []
+        for mode in (0, 1):
+            ev, V, sw = np.zeros(3), np.zeros(9), C.c_int32()
+            rc = L.ndtb_eig_sym3(A.ctypes.data, mode, ev.ctypes.data, V.ctypes.data, C.byref(sw))
+            assert rc == 1
+            out.append((ev.copy(), V.copy(), sw.value))
+        assert out[0][0].tobytes() == out[1][0].tobytes() and out[0][1].tobytes() == out[1][1].tobytes(), trial
+        evo, Vo = oracle.eig_sym(A)
+        assert np.asarray(evo).tobytes() == out[1][0].tobytes() and np.ascontiguousarray(Vo).tobytes() == out[1][1].tobytes(), trial
+        if out[0][2] == 64:
+            n_never += 1
+            max_fixed = max(max_fixed, out[1][2])
+            assert out[1][2] <= 20
+        else:
+            assert out[1][2] == out[0][2]
+    assert n_never > 50 and max_fixed <= 16
